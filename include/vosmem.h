@@ -1,0 +1,193 @@
+/*
+ * vosmem.h -- C ABI of the B200-native space-time memory readout (libvosmem.so).
+ *
+ * The reference (jpitagc/VOS-E-SAM, XMem tracker) has no FFI layer: its hot path is Python
+ * calling torch ops.  This header is the boundary a maintainer binds instead -- plain device
+ * pointers, sizes and a cudaStream_t (passed as void*), no torch types.  Every entry point
+ * names the reference lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; fp32 unless stated otherwise
+ *   - functions only enqueue work on `stream`; they never synchronise, never allocate
+ *   - return 0 on success, a negative VOSMEM_E* code otherwise; vosmem_last_error() gives
+ *     a thread-local message.  No C++ exception crosses this boundary.
+ *   - "key axis" = memory elements N (reference: last dim of k / v), "query axis" = HW
+ *   - matrices named like the reference: key is CK x N with N contiguous (row pitch key_ld),
+ *     queries are CK x HW with HW contiguous, values are rows x N with N contiguous.
+ */
+#ifndef VOSMEM_H_
+#define VOSMEM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOSMEM_ABI_VERSION 1
+
+typedef void *vosmem_stream_t; /* cudaStream_t */
+
+enum vosmem_status {
+  VOSMEM_OK = 0,
+  VOSMEM_EINVAL = -22,  /* bad argument (shape, null pointer, unsupported top_k ...) */
+  VOSMEM_ENOTSUP = -95, /* configuration not supported by the requested kernel path */
+  VOSMEM_ENOSPC = -28,  /* workspace too small */
+  VOSMEM_ECUDA = -5     /* a CUDA runtime call failed (message has the CUDA error string) */
+};
+
+enum vosmem_dtype { VOSMEM_F32 = 0, VOSMEM_BF16 = 1 };
+
+/* kernel path for the similarity + selection stage */
+enum vosmem_path {
+  VOSMEM_PATH_AUTO = 0,   /* tcgen05 when CK == 64, else SIMT */
+  VOSMEM_PATH_SIMT = 1,   /* exact fp32 CUDA-core kernel, any CK <= 256 */
+  VOSMEM_PATH_TCGEN05 = 2 /* TMA(bulk) + tcgen05/TMEM kernel, CK == 64 */
+};
+
+#define VOSMEM_MAX_TOPK 32     /* per-query survivors held one per lane of a warp */
+#define VOSMEM_KEY_TILE 64     /* keys per packed image tile */
+#define VOSMEM_QUERY_TILE 128  /* queries per packed image tile (= TMEM lanes) */
+#define VOSMEM_MAX_SEGMENTS 2  /* [long-term | working] */
+
+int vosmem_abi_version(void);
+const char *vosmem_last_error(void);
+const char *vosmem_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout helpers (host-only arithmetic; usable without a GPU).
+ * ------------------------------------------------------------------------------------------- */
+
+/* bytes of the packed key image holding `capacity` keys (rounded up to VOSMEM_KEY_TILE) */
+int64_t vosmem_key_image_bytes(int ck, int64_t capacity);
+/* scratch bytes vosmem_select_topk / vosmem_match need for `hw` queries over `n_keys` keys */
+int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys);
+
+/* ---------------------------------------------------------------------------------------------
+ * Store-side packing.  Replaces the torch.cat growth of KeyValueMemoryStore.add
+ * (tracker/inference/kv_memory_store.py:36-90): the store owns preallocated buffers and packs
+ * only the appended range.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Pack keys [begin, end) of a bank into the tensor-core operand image.
+ * Row n of the operand is  s[n]/sqrt(CK) * [ k[:,n]^2 , k[:,n] , 1 ]  split into bf16 hi/lo halves
+ * (memory_util.py:24-25,35: the shrinkage scale is folded into the memory side).
+ * shrinkage may be NULL (memory_util.py:36-37).  Only CK == 64 has an image format. */
+int vosmem_pack_keys(const float *key, int64_t key_ld, const float *shrinkage, int ck, int64_t begin,
+                     int64_t end, void *image, int64_t capacity, vosmem_stream_t stream);
+
+/* Transpose-append values into the gather-friendly shadow:
+ *   shadow[(dst_begin + i) * shadow_ld + r] = value[r * value_ld + src_begin + i],  r < rows, i < n
+ * (the reference keeps values rows x N and concatenates on N: kv_memory_store.py:70,88). */
+int vosmem_pack_values(const float *value, int64_t value_ld, int rows, int64_t src_begin, int64_t n,
+                       void *shadow, int64_t shadow_ld, int64_t dst_begin, int shadow_dtype,
+                       vosmem_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The hot path: MemoryManager.match_memory for one object group
+ * (tracker/inference/memory_manager.py:57-150 driving memory_util.py:7-65).
+ * ------------------------------------------------------------------------------------------- */
+
+/* One contiguous candidate range of one bank ([long-term] or [working]). */
+typedef struct vosmem_segment {
+  const float *key;       /* CK x N fp32, row pitch key_ld              (SIMT path)            */
+  int64_t key_ld;
+  const float *shrinkage; /* N fp32 or NULL                              (SIMT path)            */
+  const void *key_image;  /* packed image from vosmem_pack_keys or NULL  (tcgen05 path)         */
+  int64_t begin, end;     /* candidate keys [begin, end) of the bank; a group that entered the
+                             video late only sees a suffix (memory_manager.py:88-98,137-140)   */
+} vosmem_segment;
+
+/* Similarity + per-query top-k.  Candidate index = position on the concatenated candidate axis
+ * [seg0 | seg1] plus index_base (a rank's offset when the bank is sharded along N). */
+typedef struct vosmem_select_desc {
+  int ck, hw, top_k;
+  const float *query_key;       /* CK x HW                                                     */
+  const float *query_selection; /* CK x HW or NULL (memory_util.py:28-32)                      */
+  int n_segments;
+  vosmem_segment seg[VOSMEM_MAX_SEGMENTS];
+  int64_t index_base;
+  int path;                     /* enum vosmem_path                                            */
+  void *workspace;
+  int64_t workspace_bytes;
+} vosmem_select_desc;
+
+/* out_score / out_index: HW x top_k, sorted by descending score; missing candidates (fewer than
+ * top_k keys) are (-inf, -1).  Replaces get_similarity + torch.topk (memory_util.py:7-39,46)
+ * without materialising the N x HW matrix. */
+int vosmem_select_topk(const vosmem_select_desc *desc, float *out_score, int64_t *out_index,
+                       vosmem_stream_t stream);
+
+/* Merge `n_lists` candidate lists (each HW x top_k, e.g. one per rank after an all-gather) into the
+ * global top_k per query.  lists are laid out [list][HW][top_k]. */
+int vosmem_merge_topk(const float *scores, const int64_t *indices, int n_lists, int hw, int top_k,
+                      float *out_score, int64_t *out_index, vosmem_stream_t stream);
+
+/* Values of one object group on the candidate axis. */
+typedef struct vosmem_value_segment {
+  const void *shadow;   /* rows of n_g*CV values per memory element (vosmem_pack_values layout) */
+  int64_t shadow_ld;    /* elements between consecutive memory elements                         */
+  int64_t first;        /* global candidate index of shadow row 0                               */
+  int64_t count;        /* candidates [first, first+count) live in this shadow                  */
+  float *use_count;     /* += sum_q affinity[n, q]   or NULL (kv_memory_store.py:92-99)         */
+} vosmem_value_segment;
+
+typedef struct vosmem_readout_desc {
+  int hw, top_k;
+  int rows;             /* n_g * CV                                                            */
+  int value_dtype;      /* enum vosmem_dtype of the shadows                                    */
+  int n_segments;
+  vosmem_value_segment seg[VOSMEM_MAX_SEGMENTS];
+  float *out;           /* rows x HW, row pitch out_ld (the reference's n_g x CV x h x w)      */
+  int64_t out_ld;
+  float *out_weight;    /* optional HW x top_k softmax weights, or NULL                        */
+} vosmem_readout_desc;
+
+/* softmax over the top_k survivors (max-subtracted; memory_util.py:48-49), usage scatter-add
+ * (memory_util.py:62-63) and the affinity x value product restricted to the survivors
+ * (memory_manager.py:53-55,145-148).  Candidates whose index falls outside every value segment
+ * contribute to the softmax normalisation but not to `out` (values held by another rank). */
+int vosmem_softmax_readout(const vosmem_readout_desc *desc, const float *score, const int64_t *index,
+                           vosmem_stream_t stream);
+
+/* select + softmax + readout for one group in one call (what match_memory does per group). */
+int vosmem_match(const vosmem_select_desc *select, const vosmem_readout_desc *readout,
+                 float *scratch_score, int64_t *scratch_index, vosmem_stream_t stream);
+
+/* life_count[0:n] += 1  (kv_memory_store.py:99) */
+int vosmem_age(float *life_count, int64_t n, vosmem_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense twins of tracker/model/memory_util.py, for API parity (training-time read_memory,
+ * memory consolidation).  Batch 1; callers loop over B.
+ * ------------------------------------------------------------------------------------------- */
+
+/* get_similarity (memory_util.py:7-39): out is N x HW, row pitch hw. shrinkage / selection may be NULL */
+int vosmem_similarity_dense(const float *key, int64_t key_ld, const float *shrinkage, const float *query_key,
+                            const float *query_selection, int ck, int64_t n, int hw, float *out,
+                            vosmem_stream_t stream);
+
+/* do_softmax (memory_util.py:41-65) over the key axis of an N x HW matrix (row pitch sim_ld).
+ * top_k <= 0 means the max-subtracted dense softmax; usage (N) may be NULL.  affinity may alias
+ * similarity (the reference's inplace=True). */
+int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k, float *affinity,
+                         int64_t aff_ld, float *usage, vosmem_stream_t stream);
+
+/* readout / MemoryManager._readout (memory_util.py:73-80, memory_manager.py:53-55):
+ * out[rows x hw] = value[rows x n] @ affinity[n x hw] */
+int vosmem_readout_dense(const float *value, int64_t value_ld, const float *affinity, int64_t aff_ld, int rows,
+                         int64_t n, int hw, float *out, int64_t out_ld, vosmem_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-test hook: D[128 x 64] = A[128 x 272] . B[64 x 272]^T through the same descriptors the
+ * tcgen05 path uses, on packed images.  Returns the raw accumulator tile (fp32, 128 x 64).
+ * ------------------------------------------------------------------------------------------- */
+int vosmem_debug_umma_tile(const void *query_image, const void *key_image, float *out, vosmem_stream_t stream);
+int vosmem_debug_pack_query(const float *query_key, const float *query_selection, int ck, int hw, void *image,
+                            vosmem_stream_t stream);
+int64_t vosmem_query_image_bytes(int ck, int hw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOSMEM_H_ */

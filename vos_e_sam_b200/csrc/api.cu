@@ -1,0 +1,130 @@
+// extern "C" entry points that tie the kernels into the calls declared in include/vosmem.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vosmem {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+// N-splits so that (query tiles x splits) fills the 148 SMs once (tcgen05: one CTA per SM) or gives the
+// SIMT kernel ~32 warps per SM; never fewer than ~4 key tiles per split.
+int choose_splits(int path, int hw, int64_t n_total) {
+  const int cap = splits_cap(hw);
+  int64_t s;
+  if (path == VOSMEM_PATH_TCGEN05) {
+    int64_t n_qtiles = ceil_div64(hw, TQ);
+    s = 148 / n_qtiles;
+    int64_t by_tiles = ceil_div64(n_total, TK) / 4;
+    if (s > by_tiles) s = by_tiles;
+    int64_t need = ceil_div64(ceil_div64(n_total, TK) + 2, 1024);  // 16-bit candidate index inside a CTA
+    if (s < need) s = need;
+  } else {
+    s = ceil_div64(4736, hw);
+    int64_t by_keys = n_total / 256;
+    if (s > by_keys) s = by_keys;
+  }
+  if (s < 1) s = 1;
+  if (s > cap) s = cap;
+  return (int)s;
+}
+
+static int resolve_path(const vosmem_select_desc &d) {
+  if (d.path == VOSMEM_PATH_SIMT || d.path == VOSMEM_PATH_TCGEN05) return d.path;
+  if (d.ck != CK_TC) return VOSMEM_PATH_SIMT;
+  for (int s = 0; s < d.n_segments; ++s)
+    if (d.seg[s].end > d.seg[s].begin && d.seg[s].key_image == nullptr) return VOSMEM_PATH_SIMT;
+  return VOSMEM_PATH_TCGEN05;
+}
+
+static int validate_select(const vosmem_select_desc *d) {
+  VOSMEM_CHECK_ARG(d != nullptr, "select: null descriptor");
+  VOSMEM_CHECK_ARG(d->ck >= 1 && d->ck <= 256, "select: CK=%d outside [1, 256]", d->ck);
+  VOSMEM_CHECK_ARG(d->hw >= 1, "select: HW=%d", d->hw);
+  VOSMEM_CHECK_ARG(d->top_k >= 1 && d->top_k <= VOSMEM_MAX_TOPK, "select: top_k=%d outside [1, %d]", d->top_k,
+                   VOSMEM_MAX_TOPK);
+  VOSMEM_CHECK_ARG(d->query_key != nullptr, "select: null query_key");
+  VOSMEM_CHECK_ARG(d->n_segments >= 1 && d->n_segments <= VOSMEM_MAX_SEGMENTS, "select: n_segments=%d", d->n_segments);
+  int64_t total = 0;
+  for (int s = 0; s < d->n_segments; ++s) {
+    VOSMEM_CHECK_ARG(d->seg[s].begin >= 0 && d->seg[s].end >= d->seg[s].begin, "select: segment %d range [%lld, %lld)",
+                     s, (long long)d->seg[s].begin, (long long)d->seg[s].end);
+    total += d->seg[s].end - d->seg[s].begin;
+  }
+  VOSMEM_CHECK_ARG(total >= 1, "select: no memory elements");
+  VOSMEM_CHECK_ARG(total < (int64_t)0x7fffffff, "select: %lld memory elements exceed the 31-bit candidate index",
+                   (long long)total);
+  VOSMEM_CHECK_ARG(d->workspace != nullptr, "select: null workspace");
+  if (d->workspace_bytes < vosmem_workspace_bytes(d->ck, d->hw, total)) {
+    set_error("select: workspace of %lld bytes, need %lld", (long long)d->workspace_bytes,
+              (long long)vosmem_workspace_bytes(d->ck, d->hw, total));
+    return VOSMEM_ENOSPC;
+  }
+  return VOSMEM_OK;
+}
+
+}  // namespace vosmem
+
+using namespace vosmem;
+
+extern "C" int vosmem_abi_version(void) { return VOSMEM_ABI_VERSION; }
+extern "C" const char *vosmem_last_error(void) { return g_error; }
+extern "C" const char *vosmem_status_string(int status) {
+  switch (status) {
+    case VOSMEM_OK: return "ok";
+    case VOSMEM_EINVAL: return "invalid argument";
+    case VOSMEM_ENOTSUP: return "not supported";
+    case VOSMEM_ENOSPC: return "workspace too small";
+    case VOSMEM_ECUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int64_t vosmem_key_image_bytes(int ck, int64_t capacity) {
+  if (ck != CK_TC || capacity < 0) return 0;
+  return ceil_div64(capacity, TK) * (int64_t)KEY_TILE_BYTES;
+}
+
+extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
+  (void)n_keys;
+  if (ck < 1 || hw < 1) return 0;
+  return carve_workspace(nullptr, ck, hw).bytes;
+}
+
+extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score, int64_t *out_index,
+                                  vosmem_stream_t stream) {
+  int rc = validate_select(d);
+  if (rc != VOSMEM_OK) return rc;
+  VOSMEM_CHECK_ARG(out_score && out_index, "select: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Workspace ws = carve_workspace(d->workspace, d->ck, d->hw);
+  int64_t total = 0;
+  for (int s = 0; s < d->n_segments; ++s) total += d->seg[s].end - d->seg[s].begin;
+  const int path = resolve_path(*d);
+  const int splits = choose_splits(path, d->hw, total);
+  rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
+  if (rc != VOSMEM_OK) return rc;
+  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(*d, ws, splits, st) : launch_select_simt(*d, ws, splits, st);
+  if (rc != VOSMEM_OK) return rc;
+  return launch_merge_splits(ws, splits, d->hw, d->top_k, d->index_base, out_score, out_index, st);
+}
+
+extern "C" int vosmem_match(const vosmem_select_desc *select, const vosmem_readout_desc *readout, float *scratch_score,
+                            int64_t *scratch_index, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(select && readout, "vosmem_match: null descriptor");
+  VOSMEM_CHECK_ARG(select->hw == readout->hw && select->top_k == readout->top_k,
+                   "vosmem_match: select (hw=%d, k=%d) and readout (hw=%d, k=%d) disagree", select->hw, select->top_k,
+                   readout->hw, readout->top_k);
+  int rc = vosmem_select_topk(select, scratch_score, scratch_index, stream);
+  if (rc != VOSMEM_OK) return rc;
+  return vosmem_softmax_readout(readout, scratch_score, scratch_index, stream);
+}

@@ -1,0 +1,191 @@
+// Shared device helpers for the memory-readout kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vosmem.h"
+
+namespace vosmem {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CK_TC = 64;                       // channel count the tensor-core image is built for
+constexpr int TK = VOSMEM_KEY_TILE;             // keys per image tile
+constexpr int TQ = VOSMEM_QUERY_TILE;           // queries per image tile
+constexpr int K8 = 34;                          // 16-byte K chunks per operand row: 16 hi + 16 lo + 2 tail
+constexpr int KEY_TILE_BYTES = K8 * (TK / 8) * 128;    // 34816
+constexpr int QUERY_TILE_BYTES = K8 * (TQ / 8) * 128;  // 69632
+constexpr int CAND_SLOTS = 64;                  // per (split, query) candidate slots in the exchange buffer
+constexpr int MAX_SPLITS = 32;
+
+void set_error(const char *fmt, ...);
+#define VOSMEM_CHECK_ARG(cond, ...)              \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::vosmem::set_error(__VA_ARGS__);          \
+      return VOSMEM_EINVAL;                      \
+    }                                            \
+  } while (0)
+#define VOSMEM_CUDA(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      ::vosmem::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return VOSMEM_ECUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
+
+// ------------------------------------------------------------------------------------------------
+// order-preserving float <-> uint map (for atomicMax on thresholds)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+constexpr unsigned ORD_NEG_INF = 0x007fffffu;   // f2ord(-inf)
+
+// ------------------------------------------------------------------------------------------------
+// A candidate is (score, index); "better" = higher score, ties to the lower index (total order, so
+// every sort below is deterministic).
+__device__ __forceinline__ bool better(float s, int i, float os, int oi) { return s > os || (s == os && i < oi); }
+
+// compare-exchange with lane ^ j; keep_best: this lane keeps the better of the pair
+__device__ __forceinline__ void cmpx(float &s, int &i, int j, bool keep_best) {
+  float os = __shfl_xor_sync(FULL, s, j);
+  int oi = __shfl_xor_sync(FULL, i, j);
+  bool mine = better(s, i, os, oi);
+  if (mine != keep_best) { s = os; i = oi; }
+}
+
+// Sort 32 candidates (one per lane) best-first.
+__device__ __forceinline__ void warp_sort_desc(float &s, int &i, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      bool desc = (k == 32) || ((lane & k) == 0);
+      bool low = (lane & j) == 0;
+      cmpx(s, i, j, low == desc);
+    }
+  }
+}
+
+// Bitonic sequence across lanes -> best-first.
+__device__ __forceinline__ void warp_bitonic_merge_desc(float &s, int &i, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) cmpx(s, i, j, (lane & j) == 0);
+}
+
+// Running best-32 of a stream, one survivor per lane, best-first.  `push` takes one candidate per
+// lane; it costs one vote when nothing beats the current 32nd.
+struct WarpTop32 {
+  float s;
+  int i;
+  __device__ __forceinline__ void init() { s = -INFINITY; i = 0x7fffffff; }
+  __device__ __forceinline__ float floor_score() const { return __shfl_sync(FULL, s, 31); }
+  __device__ __forceinline__ void push(float cs, int ci, int lane) {
+    float tau = __shfl_sync(FULL, s, 31);
+    int ti = __shfl_sync(FULL, i, 31);
+    if (!__any_sync(FULL, better(cs, ci, tau, ti))) return;
+    warp_sort_desc(cs, ci, lane);
+    // reverse the batch so list (descending) ++ batch (ascending) is bitonic, keep the better half
+    float rs = __shfl_sync(FULL, cs, 31 - lane);
+    int ri = __shfl_sync(FULL, ci, 31 - lane);
+    if (better(rs, ri, s, i)) { s = rs; i = ri; }
+    warp_bitonic_merge_desc(s, i, lane);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) v += __shfl_xor_sync(FULL, v, j);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, j));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, j));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 hi/lo split: v ~= hi + lo with ~16 mantissa bits
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// byte offset of (row r, 16-byte chunk k8) inside an operand tile image of ROWS rows
+template <int ROWS>
+__host__ __device__ inline int image_offset(int r, int k8) {
+  return (k8 * (ROWS / 8) + (r >> 3)) * 128 + (r & 7) * 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace carving shared by host and kernels.
+struct Workspace {
+  unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
+  unsigned *tau;               // hw_pad  (order-encoded running lower bound of the k-th score)
+  float *cand_score;           // splits * hw_pad * CAND_SLOTS
+  int *cand_index;             // splits * hw_pad * CAND_SLOTS
+  int *cand_count;             // splits * hw_pad
+  float *qvec;                 // SIMT path: hw * (2*ck + 1)  [-e | 2*q*e | -sum e q^2]
+  int64_t bytes;
+};
+
+// Upper bound on the N-splits either kernel path will ever use for `hw` queries (sizes the exchange buffers).
+inline int splits_cap(int hw) {
+  int64_t n_qtiles = ceil_div64(hw, TQ);
+  int64_t a = 148 / n_qtiles, b = ceil_div64(4736, hw);
+  int64_t s = a > b ? a : b;
+  if (s < 4) s = 4;  // room for >65536 keys per launch (16-bit in-CTA candidate index)
+  if (s > MAX_SPLITS) s = MAX_SPLITS;
+  return (int)s;
+}
+
+inline Workspace carve_workspace(void *base, int ck, int hw) {
+  Workspace w;
+  const int64_t cap = splits_cap(hw);
+  int64_t n_qtiles = ceil_div64(hw, TQ);
+  int64_t hw_pad = n_qtiles * TQ;
+  unsigned char *p = static_cast<unsigned char *>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    unsigned char *r = p ? p + off : nullptr;
+    off += round_up64(bytes, 256);
+    return r;
+  };
+  w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
+  w.tau = reinterpret_cast<unsigned *>(take(hw_pad * 4));
+  w.cand_score = reinterpret_cast<float *>(take(cap * hw_pad * CAND_SLOTS * 4));
+  w.cand_index = reinterpret_cast<int *>(take(cap * hw_pad * CAND_SLOTS * 4));
+  w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));
+  w.qvec = reinterpret_cast<float *>(take((int64_t)hw_pad * (2 * ck + 1) * 4));
+  w.bytes = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers implemented in the .cu files
+struct SelectPlan {
+  int splits;          // N-splits (gridDim.y)
+  int64_t n_total;     // candidates over all segments
+};
+
+int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st);
+int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
+int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
+int launch_merge_splits(const Workspace &ws, int splits, int hw, int top_k, int64_t index_base, float *out_score,
+                        int64_t *out_index, cudaStream_t st);
+int choose_splits(int path, int hw, int64_t n_total);
+
+}  // namespace vosmem

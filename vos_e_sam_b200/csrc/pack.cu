@@ -1,0 +1,223 @@
+// Operand packing: keys / queries -> tensor-core images, values -> gather-friendly shadow.
+//
+// Reference math (tracker/model/memory_util.py:20-27,35):
+//   S[n,q] = s[n]/sqrt(CK) * ( -sum_c k[c,n]^2 e[c,q] + 2 sum_c k[c,n] q[c,q] e[c,q] - sum_c e[c,q] q[c,q]^2 )
+// is one inner product of length 2*CK+1 between
+//   key row   x[n] = s[n]/sqrt(CK) * [ k^2 , k , 1 ]          (packed once per memory frame)
+//   query row y[q] =                 [ -e  , 2 q e , -sum e q^2 ]   (packed once per query frame)
+// Each fp32 entry is stored as a bf16 (hi, lo) pair; the kernel accumulates hi*hi + hi*lo + lo*hi
+// in fp32, which keeps ~16 mantissa bits per factor (measured score error ~1e-4 on N(0,1) inputs).
+#include "common.cuh"
+
+namespace vosmem {
+
+namespace {
+
+struct Chunk8 {
+  __nv_bfloat16 v[8];
+};
+static_assert(sizeof(Chunk8) == 16, "chunk must be one 16-byte core-matrix row");
+
+__device__ __forceinline__ void store_chunk(unsigned char *tile, int off, const Chunk8 &c) {
+  *reinterpret_cast<uint4 *>(tile + off) = *reinterpret_cast<const uint4 *>(&c);
+}
+
+// One thread per key.  Image chunk order per row: [x1_hi 0-7 | x2_hi 8-15 | x1_lo 16-23 | x2_lo 24-31 | tail 32 | 0 33]
+// with x1 = c*k^2, x2 = c*k, tail = (c_hi, c_hi, c_lo, 0...).
+__global__ void pack_keys_kernel(const float *__restrict__ key, int64_t key_ld, const float *__restrict__ shrinkage,
+                                 int64_t begin, int64_t end, unsigned char *__restrict__ image) {
+  int64_t n = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= end) return;
+  const float scale = (shrinkage ? shrinkage[n] : 1.0f) * 0.125f;  // 1/sqrt(64)
+  unsigned char *tile = image + (n / TK) * (int64_t)KEY_TILE_BYTES;
+  const int r = (int)(n % TK);
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    Chunk8 h1, l1, h2, l2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float m = key[(int64_t)(g * 8 + j) * key_ld + n];
+      float x2 = scale * m;
+      float x1 = x2 * m;
+      split_bf16(x1, h1.v[j], l1.v[j]);
+      split_bf16(x2, h2.v[j], l2.v[j]);
+    }
+    store_chunk(tile, image_offset<TK>(r, g), h1);
+    store_chunk(tile, image_offset<TK>(r, 8 + g), h2);
+    store_chunk(tile, image_offset<TK>(r, 16 + g), l1);
+    store_chunk(tile, image_offset<TK>(r, 24 + g), l2);
+  }
+  Chunk8 t;
+  __nv_bfloat16 hi, lo;
+  split_bf16(scale, hi, lo);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+  t.v[0] = hi; t.v[1] = hi; t.v[2] = lo;
+  store_chunk(tile, image_offset<TK>(r, 32), t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+  store_chunk(tile, image_offset<TK>(r, 33), t);
+}
+
+// One thread per (padded) query: fp32 vector for the SIMT path, bf16 image for the tcgen05 path, and
+// the per-query threshold reset.  Image chunk order: [y1_hi | y2_hi | y1_lo | y2_lo | tail | 0] with
+// y1 = -e, y2 = 2 q e, tail = (y3_hi, y3_lo, y3_hi, 0...), y3 = -sum e q^2.
+__global__ void pack_query_kernel(const float *__restrict__ qk, const float *__restrict__ qe, int ck, int hw,
+                                  int hw_pad, float *__restrict__ qvec, unsigned char *__restrict__ image,
+                                  unsigned *__restrict__ tau) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= hw_pad) return;
+  tau[q] = ORD_NEG_INF;
+  const bool live = q < hw;
+  const bool img = (ck == CK_TC);
+  unsigned char *tile = image + (int64_t)(q / TQ) * QUERY_TILE_BYTES;
+  const int r = q % TQ;
+  float *vec = qvec + (int64_t)q * (2 * ck + 1);
+  float y3 = 0.f;
+  for (int g = 0; g < ck / 8 + (ck % 8 != 0); ++g) {
+    Chunk8 h1, l1, h2, l2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = g * 8 + j;
+      float y1 = 0.f, y2 = 0.f;
+      if (live && c < ck) {
+        float k = qk[(int64_t)c * hw + q];
+        float e = qe ? qe[(int64_t)c * hw + q] : 1.0f;
+        y1 = -e;
+        y2 = 2.0f * (k * e);
+        if (qe) y3 -= e * (k * k);
+      }
+      if (c < ck) {
+        vec[c] = y1;
+        vec[ck + c] = y2;
+      }
+      split_bf16(y1, h1.v[j], l1.v[j]);
+      split_bf16(y2, h2.v[j], l2.v[j]);
+    }
+    if (img) {
+      store_chunk(tile, image_offset<TQ>(r, g), h1);
+      store_chunk(tile, image_offset<TQ>(r, 8 + g), h2);
+      store_chunk(tile, image_offset<TQ>(r, 16 + g), l1);
+      store_chunk(tile, image_offset<TQ>(r, 24 + g), l2);
+    }
+  }
+  vec[2 * ck] = y3;
+  if (img) {
+    Chunk8 t;
+    __nv_bfloat16 hi, lo;
+    split_bf16(y3, hi, lo);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+    t.v[0] = hi; t.v[1] = lo; t.v[2] = hi;
+    store_chunk(tile, image_offset<TQ>(r, 32), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+    store_chunk(tile, image_offset<TQ>(r, 33), t);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T to_store(float v);
+template <>
+__device__ __forceinline__ float to_store<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_store<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 32 x 32 transpose through shared memory: rows x N (N contiguous) -> N x rows (rows contiguous)
+template <typename T>
+__global__ void pack_values_kernel(const float *__restrict__ value, int64_t value_ld, int rows, int64_t src_begin,
+                                   int64_t n, T *__restrict__ shadow, int64_t shadow_ld, int64_t dst_begin) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    int r = r0 + dy;
+    int64_t i = i0 + threadIdx.x;
+    tile[dy][threadIdx.x] = (r < rows && i < n) ? value[(int64_t)r * value_ld + src_begin + i] : 0.f;
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    int64_t i = i0 + dy;
+    int r = r0 + threadIdx.x;
+    if (r < rows && i < n) shadow[(dst_begin + i) * shadow_ld + r] = to_store<T>(tile[threadIdx.x][dy]);
+  }
+}
+
+__global__ void age_kernel(float *__restrict__ life, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) life[i] += 1.0f;
+}
+
+}  // namespace
+
+int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st) {
+  int hw_pad = (int)round_up64(hw, TQ);
+  pack_query_kernel<<<(hw_pad + 127) / 128, 128, 0, st>>>(qk, qe, ck, hw, hw_pad, ws.qvec, ws.query_image, ws.tau);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+}  // namespace vosmem
+
+using namespace vosmem;
+
+extern "C" int vosmem_pack_keys(const float *key, int64_t key_ld, const float *shrinkage, int ck, int64_t begin,
+                                int64_t end, void *image, int64_t capacity, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(ck == CK_TC, "vosmem_pack_keys: the tensor-core image exists for CK == 64 only (got %d)", ck);
+  VOSMEM_CHECK_ARG(key && image, "vosmem_pack_keys: null pointer");
+  VOSMEM_CHECK_ARG(0 <= begin && begin <= end && end <= round_up64(capacity, TK),
+                   "vosmem_pack_keys: range [%lld, %lld) outside capacity %lld", (long long)begin, (long long)end,
+                   (long long)capacity);
+  if (begin == end) return VOSMEM_OK;
+  int64_t n = end - begin;
+  pack_keys_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      key, key_ld, shrinkage, begin, end, static_cast<unsigned char *>(image));
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+extern "C" int vosmem_pack_values(const float *value, int64_t value_ld, int rows, int64_t src_begin, int64_t n,
+                                  void *shadow, int64_t shadow_ld, int64_t dst_begin, int shadow_dtype,
+                                  vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(value && shadow, "vosmem_pack_values: null pointer");
+  VOSMEM_CHECK_ARG(rows > 0 && n >= 0 && shadow_ld >= rows, "vosmem_pack_values: bad shape rows=%d n=%lld ld=%lld",
+                   rows, (long long)n, (long long)shadow_ld);
+  VOSMEM_CHECK_ARG(shadow_dtype == VOSMEM_F32 || shadow_dtype == VOSMEM_BF16, "vosmem_pack_values: bad dtype %d",
+                   shadow_dtype);
+  if (n == 0) return VOSMEM_OK;
+  dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+  if (shadow_dtype == VOSMEM_F32)
+    pack_values_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(value, value_ld, rows, src_begin, n,
+                                                                        static_cast<float *>(shadow), shadow_ld, dst_begin);
+  else
+    pack_values_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
+        value, value_ld, rows, src_begin, n, static_cast<__nv_bfloat16 *>(shadow), shadow_ld, dst_begin);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+extern "C" int vosmem_age(float *life_count, int64_t n, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(life_count || n == 0, "vosmem_age: null pointer");
+  if (n <= 0) return VOSMEM_OK;
+  age_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(life_count, n);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+extern "C" int vosmem_debug_pack_query(const float *query_key, const float *query_selection, int ck, int hw,
+                                       void *image, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(ck == CK_TC && query_key && image, "vosmem_debug_pack_query: CK must be 64, pointers non-null");
+  // image buffer layout: [query image tiles | tau (hw_pad) | qvec]; see vosmem_query_image_bytes
+  Workspace ws{};
+  int64_t n_qtiles = ceil_div64(hw, TQ), hw_pad = n_qtiles * TQ;
+  unsigned char *p = static_cast<unsigned char *>(image);
+  ws.query_image = p;
+  ws.tau = reinterpret_cast<unsigned *>(p + n_qtiles * QUERY_TILE_BYTES);
+  ws.qvec = reinterpret_cast<float *>(p + n_qtiles * QUERY_TILE_BYTES + hw_pad * 4);
+  return launch_pack_query(query_key, query_selection, ck, hw, ws, (cudaStream_t)stream);
+}
+
+extern "C" int64_t vosmem_query_image_bytes(int ck, int hw) {
+  int64_t n_qtiles = ceil_div64(hw, TQ), hw_pad = n_qtiles * TQ;
+  return n_qtiles * QUERY_TILE_BYTES + hw_pad * 4 + hw_pad * (2 * (int64_t)ck + 1) * 4;
+}

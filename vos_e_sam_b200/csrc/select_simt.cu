@@ -1,0 +1,186 @@
+// Exact fp32 similarity + per-query top-k on CUDA cores, and the split/rank merge kernels.
+//
+// This is the any-CK path (and the on-device cross-check for the tcgen05 path): one warp per query,
+// lanes stride over memory keys, the warp keeps a running best-32 (WarpTop32).  The N x HW similarity
+// matrix of the reference (memory_util.py:7-39) is never written.
+#include "common.cuh"
+
+namespace vosmem {
+
+namespace {
+
+struct SimtSeg {
+  const float *key;
+  int64_t key_ld;
+  const float *shrinkage;
+  int64_t begin;  // first candidate key of the bank
+};
+
+struct SimtArgs {
+  SimtSeg seg[2];
+  int64_t len0, n_total;  // candidates in seg0, in total
+  int ck, hw, hw_pad, splits;
+  float inv_sqrt_ck;
+  const float *qvec;
+  float *cand_score;
+  int *cand_index;
+  int *cand_count;
+};
+
+constexpr int SIMT_WARPS = 8;
+
+__global__ void __launch_bounds__(SIMT_WARPS * 32) select_simt_kernel(SimtArgs a) {
+  extern __shared__ float smem[];  // SIMT_WARPS * (2*ck+1)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * SIMT_WARPS + warp;
+  const int vlen = 2 * a.ck + 1;
+  float *qv = smem + warp * vlen;
+  if (q < a.hw)
+    for (int c = lane; c < vlen; c += 32) qv[c] = a.qvec[(int64_t)q * vlen + c];
+  __syncwarp();
+  if (q >= a.hw) return;
+
+  // candidate range of this split, in whole warps of 32
+  const int64_t per = ceil_div64(ceil_div64(a.n_total, a.splits), 32) * 32;
+  const int64_t lo = per * blockIdx.y;
+  const int64_t hi = lo + per < a.n_total ? lo + per : a.n_total;
+
+  WarpTop32 top;
+  top.init();
+  const float y3 = qv[2 * a.ck];
+  for (int64_t base = lo; base < hi; base += 32) {
+    const int64_t cand = base + lane;
+    const bool valid = cand < hi;
+    float score = -INFINITY;
+    if (valid) {
+      const int s = cand >= a.len0;
+      const SimtSeg &sg = a.seg[s];
+      const int64_t n = sg.begin + (s ? cand - a.len0 : cand);
+      const float *kp = sg.key + n;
+      float acc1 = 0.f, acc2 = 0.f;  // two chains for ILP
+#pragma unroll 4
+      for (int c = 0; c < a.ck; ++c) {
+        float m = kp[(int64_t)c * sg.key_ld];
+        acc1 = fmaf(m * m, qv[c], acc1);
+        acc2 = fmaf(m, qv[a.ck + c], acc2);
+      }
+      const float scale = (sg.shrinkage ? sg.shrinkage[n] : 1.0f) * a.inv_sqrt_ck;
+      score = (acc1 + acc2 + y3) * scale;
+    }
+    top.push(score, valid ? (int)cand : 0x7fffffff, lane);
+  }
+  const int64_t slot = ((int64_t)blockIdx.y * a.hw_pad + q) * CAND_SLOTS;
+  a.cand_score[slot + lane] = top.s;
+  a.cand_index[slot + lane] = top.i;
+  if (lane == 0) a.cand_count[(int64_t)blockIdx.y * a.hw_pad + q] = 32;
+}
+
+// One warp per query: fold the per-split candidate lists into the exact top-k, best first.
+__global__ void merge_splits_kernel(const float *__restrict__ cand_score, const int *__restrict__ cand_index,
+                                    const int *__restrict__ cand_count, int splits, int hw, int hw_pad, int top_k,
+                                    int64_t index_base, float *__restrict__ out_score,
+                                    int64_t *__restrict__ out_index) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= hw) return;
+  WarpTop32 top;
+  top.init();
+  for (int y = 0; y < splits; ++y) {
+    const int64_t row = (int64_t)y * hw_pad + q;
+    const int cnt = cand_count[row];
+    for (int off = 0; off < cnt; off += 32) {
+      const bool valid = off + lane < cnt;
+      float s = valid ? cand_score[row * CAND_SLOTS + off + lane] : -INFINITY;
+      int i = valid ? cand_index[row * CAND_SLOTS + off + lane] : 0x7fffffff;
+      if (i == 0x7fffffff) s = -INFINITY;
+      top.push(s, i, lane);
+    }
+  }
+  if (lane < top_k) {
+    const bool have = top.i != 0x7fffffff;
+    out_score[(int64_t)q * top_k + lane] = have ? top.s : -INFINITY;
+    out_index[(int64_t)q * top_k + lane] = have ? (int64_t)top.i + index_base : -1;
+  }
+}
+
+// Merge `n_lists` already-selected lists (e.g. one per rank): lists[l][q][0..top_k)
+__global__ void merge_lists_kernel(const float *__restrict__ scores, const int64_t *__restrict__ indices, int n_lists,
+                                   int hw, int top_k, float *__restrict__ out_score, int64_t *__restrict__ out_index) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= hw) return;
+  WarpTop32 top;
+  top.init();
+  for (int l = 0; l < n_lists; ++l) {
+    const int64_t row = ((int64_t)l * hw + q) * top_k;
+    float s = -INFINITY;
+    int i = 0x7fffffff;
+    if (lane < top_k) {
+      int64_t gi = indices[row + lane];
+      if (gi >= 0) { s = scores[row + lane]; i = (int)gi; }
+    }
+    top.push(s, i, lane);
+  }
+  if (lane < top_k) {
+    const bool have = top.i != 0x7fffffff;
+    out_score[(int64_t)q * top_k + lane] = have ? top.s : -INFINITY;
+    out_index[(int64_t)q * top_k + lane] = have ? (int64_t)top.i : -1;
+  }
+}
+
+}  // namespace
+
+int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st) {
+  SimtArgs a{};
+  int64_t total = 0;
+  for (int s = 0; s < 2; ++s) {
+    if (s < d.n_segments) {
+      const vosmem_segment &g = d.seg[s];
+      VOSMEM_CHECK_ARG(g.key != nullptr || g.end == g.begin, "select(SIMT): segment %d has no fp32 keys", s);
+      a.seg[s] = SimtSeg{g.key, g.key_ld, g.shrinkage, g.begin};
+      if (s == 0) a.len0 = g.end - g.begin;
+      total += g.end - g.begin;
+    }
+  }
+  if (d.n_segments == 1) a.seg[1] = a.seg[0];
+  a.n_total = total;
+  a.ck = d.ck;
+  a.hw = d.hw;
+  a.hw_pad = (int)round_up64(d.hw, TQ);
+  a.splits = splits;
+  a.inv_sqrt_ck = 1.0f / sqrtf((float)d.ck);
+  a.qvec = ws.qvec;
+  a.cand_score = ws.cand_score;
+  a.cand_index = ws.cand_index;
+  a.cand_count = ws.cand_count;
+  dim3 grid((d.hw + SIMT_WARPS - 1) / SIMT_WARPS, splits);
+  size_t smem = (size_t)SIMT_WARPS * (2 * d.ck + 1) * sizeof(float);
+  select_simt_kernel<<<grid, SIMT_WARPS * 32, smem, st>>>(a);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+int launch_merge_splits(const Workspace &ws, int splits, int hw, int top_k, int64_t index_base, float *out_score,
+                        int64_t *out_index, cudaStream_t st) {
+  int hw_pad = (int)round_up64(hw, TQ);
+  merge_splits_kernel<<<(hw + 7) / 8, 256, 0, st>>>(ws.cand_score, ws.cand_index, ws.cand_count, splits, hw, hw_pad,
+                                                   top_k, index_base, out_score, out_index);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+}  // namespace vosmem
+
+using namespace vosmem;
+
+extern "C" int vosmem_merge_topk(const float *scores, const int64_t *indices, int n_lists, int hw, int top_k,
+                                 float *out_score, int64_t *out_index, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(scores && indices && out_score && out_index, "vosmem_merge_topk: null pointer");
+  VOSMEM_CHECK_ARG(n_lists >= 1 && hw >= 1, "vosmem_merge_topk: n_lists=%d hw=%d", n_lists, hw);
+  VOSMEM_CHECK_ARG(top_k >= 1 && top_k <= VOSMEM_MAX_TOPK, "vosmem_merge_topk: top_k=%d outside [1, %d]", top_k,
+                   VOSMEM_MAX_TOPK);
+  merge_lists_kernel<<<(hw + 7) / 8, 256, 0, (cudaStream_t)stream>>>(scores, indices, n_lists, hw, top_k, out_score,
+                                                                    out_index);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}

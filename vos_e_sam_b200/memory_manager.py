@@ -1,0 +1,238 @@
+"""Drop-in for the reference's ``MemoryManager`` (tracker/inference/memory_manager.py).
+
+Same constructor (the XMem config dict), same methods and attributes that ``InferenceCore`` touches
+(tracker/inference/inference_core.py:28,37,78,81,90,116,123,128,135): ``match_memory``, ``add_memory``,
+``create_hidden_state``, ``set_hidden``, ``get_hidden``, ``update_config``, ``work_mem``, ``long_mem``,
+``hidden``, ``CK``, ``CV``, ``H``, ``W``.
+
+``match_memory`` -- the per-frame hot path -- never builds the N x HW similarity / affinity matrices
+(memory_manager.py:76,82-99): per object group it issues ONE C call that runs
+  pack query -> fused tcgen05 similarity + candidate selection -> split merge -> softmax + usage +
+  sparse readout
+over the [long-term | working] banks in place (no torch.cat of keys, similarities or values:
+memory_manager.py:73-74,83,92-93,105).  Usage counters are updated inside the readout kernel.
+
+Optional config keys (not in the reference's YAML): ``vosmem_value_dtype`` ('bf16' default | 'fp32') --
+storage type of the gather-friendly value shadow; ``vosmem_path`` ('auto' | 'simt' | 'tcgen05').
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+
+from . import _native as N
+from . import ops
+from .kv_memory_store import KeyValueMemoryStore
+from .memory_util import do_softmax, get_similarity
+
+_VALUE_DTYPES = {'bf16': torch.bfloat16, 'bfloat16': torch.bfloat16, 'fp32': torch.float32, 'float32': torch.float32}
+_PATHS = {'auto': N.PATH_AUTO, 'simt': N.PATH_SIMT, 'tcgen05': N.PATH_TCGEN05}
+
+
+class MemoryManager:
+    """Manages working, long-term and sensory memory and the working -> long-term transition."""
+
+    def __init__(self, config):
+        self.hidden_dim = config['hidden_dim']
+        self.top_k = config['top_k']
+
+        self.enable_long_term = config['enable_long_term']
+        self.enable_long_term_usage = config['enable_long_term_count_usage']
+        if self.enable_long_term:
+            self.max_mt_frames = config['max_mid_term_frames']
+            self.min_mt_frames = config['min_mid_term_frames']
+            self.num_prototypes = config['num_prototypes']
+            self.max_long_elements = config['max_long_term_elements']
+
+        self.value_dtype = _VALUE_DTYPES[str(config.get('vosmem_value_dtype', 'bf16')).lower()]
+        self.path = _PATHS[str(config.get('vosmem_path', 'auto')).lower()]
+
+        # dimensions are inferred from the first add_memory
+        self.CK = self.CV = None
+        self.H = self.W = None
+
+        # sensory memory: one tensor for all objects, B x num_objects x CH x H x W
+        self.hidden = None
+
+        self.work_mem = KeyValueMemoryStore(count_usage=self.enable_long_term, value_dtype=self.value_dtype)
+        if self.enable_long_term:
+            self.long_mem = KeyValueMemoryStore(count_usage=self.enable_long_term_usage, value_dtype=self.value_dtype)
+
+        self.reset_config = True
+        self._scratch = None
+
+    def update_config(self, config):
+        self.reset_config = True
+        self.hidden_dim = config['hidden_dim']
+        self.top_k = config['top_k']
+
+        assert self.enable_long_term == config['enable_long_term'], 'cannot update this'
+        assert self.enable_long_term_usage == config['enable_long_term_count_usage'], 'cannot update this'
+
+        self.enable_long_term_usage = config['enable_long_term_count_usage']
+        if self.enable_long_term:
+            self.max_mt_frames = config['max_mid_term_frames']
+            self.min_mt_frames = config['min_mid_term_frames']
+            self.num_prototypes = config['num_prototypes']
+            self.max_long_elements = config['max_long_term_elements']
+
+    def _readout(self, affinity, v):
+        """Dense readout of one object group (memory_manager.py:53-55); used by consolidation."""
+        n_obj, cv, n = v.shape
+        flat = v.reshape(n_obj * cv, n) if v.is_contiguous() else v.contiguous().view(n_obj * cv, n)
+        return ops.readout_dense(flat, affinity[0]).view(n_obj, cv, -1)
+
+    # ------------------------------------------------------------------------------------------------
+    def match_memory(self, query_key, selection):
+        """query_key, selection: B x CK x H x W (B == 1)  ->  num_objects x CV x H x W  (memory_manager.py:57-150)."""
+        work = self.work_mem
+        num_groups = work.num_groups
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        if query_key.shape[0] != 1:
+            raise RuntimeError('match_memory expects batch size 1 (inference_core.py:53)')
+        qk = ops._need(query_key, 'query_key').flatten(start_dim=2)[0]
+        qe = ops._need(selection, 'selection').flatten(start_dim=2)[0] if selection is not None else None
+
+        use_long = self.enable_long_term and self.long_mem.engaged()
+        long = self.long_mem if use_long else None
+        n_work = work.size
+        n_long = long.size if use_long else 0
+        # usage is taken from the first group, which always sees every key (memory_manager.py:80-84,124-129)
+        track_work = use_long or self.enable_long_term
+        track_long = use_long and self.enable_long_term_usage
+
+        rows_total = sum(work.group_rows(gi) for gi in range(num_groups))
+        out = torch.empty((rows_total, hw), dtype=torch.float32, device=qk.device)
+        if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != qk.device:
+            self._scratch = (torch.empty((hw, self.top_k), dtype=torch.float32, device=qk.device),
+                             torch.empty((hw, self.top_k), dtype=torch.int64, device=qk.device))
+
+        row0 = 0
+        for gi in range(num_groups):
+            segments, values = [], []
+            first = 0
+            if use_long and gi < long.num_groups:
+                len_l = long.get_v_size(gi)                       # memory_manager.py:83,92
+                segments.append(long.key_segment(n_long - len_l, n_long))
+                values.append(long.value_segment(gi, 0, with_usage=(gi == 0 and track_long),
+                                                 usage_offset=n_long - len_l))
+                first = len_l
+            len_w = n_work if gi == 0 else work.get_v_size(gi)    # memory_manager.py:83,93,97,138
+            segments.append(work.key_segment(n_work - len_w, n_work))
+            values.append(work.value_segment(gi, first, with_usage=(gi == 0 and track_work),
+                                             usage_offset=n_work - len_w))
+            rows = work.group_rows(gi)
+            ops.match(qk, qe, segments, values, rows, self.top_k, out=out[row0:row0 + rows], path=self.path,
+                      scratch=self._scratch)
+            row0 += rows
+
+        # life_count += 1 on every store whose usage was recorded (kv_memory_store.py:99)
+        if track_work:
+            work.age()
+        if track_long:
+            long.age()
+
+        return out.view(rows_total // self.CV, self.CV, h, w)
+
+    # ------------------------------------------------------------------------------------------------
+    def add_memory(self, key, shrinkage, value, objects, selection=None):
+        """key 1 x CK x H x W, shrinkage 1 x 1 x H x W, value 1 x num_objects x CV x H x W (memory_manager.py:152-190)."""
+        if self.H is None or self.reset_config:
+            self.reset_config = False
+            self.H, self.W = key.shape[-2:]
+            self.HW = self.H * self.W
+            if self.enable_long_term:
+                # frames -> memory elements
+                self.min_work_elements = self.min_mt_frames * self.HW
+                self.max_work_elements = self.max_mt_frames * self.HW
+
+        key = key.flatten(start_dim=2)
+        shrinkage = shrinkage.flatten(start_dim=2)
+        value = value[0].flatten(start_dim=2)
+
+        self.CK = key.shape[1]
+        self.CV = value.shape[1]
+
+        if selection is not None:
+            if not self.enable_long_term:
+                warnings.warn('the selection factor is only needed in long-term mode', UserWarning)
+            selection = selection.flatten(start_dim=2)
+
+        self.work_mem.add(key, value, shrinkage, selection, objects)
+
+        if self.enable_long_term and self.work_mem.size >= self.max_work_elements:
+            # make room in long-term memory first, then fold the middle of working memory into prototypes
+            room = self.max_long_elements - self.num_prototypes
+            if self.long_mem.size >= room:
+                self.long_mem.remove_obsolete_features(room)
+            self.compress_features()
+
+    def create_hidden_state(self, n, sample_key):
+        """n is the TOTAL number of objects (memory_manager.py:192-203)."""
+        h, w = sample_key.shape[-2:]
+        if self.hidden is None:
+            self.hidden = torch.zeros((1, n, self.hidden_dim, h, w), device=sample_key.device)
+        elif self.hidden.shape[1] != n:
+            grown = torch.zeros((1, n - self.hidden.shape[1], self.hidden_dim, h, w), device=sample_key.device)
+            self.hidden = torch.cat([self.hidden, grown], 1)
+        assert self.hidden.shape[1] == n
+
+    def set_hidden(self, hidden):
+        self.hidden = hidden
+
+    def get_hidden(self):
+        return self.hidden
+
+    # ------------------------------------------------------------------------------------------------
+    def compress_features(self):
+        """Working -> long-term consolidation (memory_manager.py:211-241): everything except the first frame
+        and the newest min_mt_frames - 1 frames becomes `num_prototypes` prototypes."""
+        hw = self.HW
+        lo, hi = hw, -self.min_work_elements + hw
+        total = self.work_mem.size
+        candidate_value = []
+        for gv in self.work_mem.value:
+            n_g = gv.shape[-1]
+            if n_g == total or n_g > self.min_work_elements + hw:
+                candidate_value.append(gv[:, :, lo:hi])
+            else:
+                # a group that entered late and is still too short to be consolidated
+                assert hw <= n_g < total
+                candidate_value.append(None)
+
+        prototype_key, prototype_value, prototype_shrinkage = self.consolidation(
+            *self.work_mem.get_all_sliced(lo, hi), candidate_value)
+
+        self.work_mem.sieve_by_range(lo, hi, min_size=self.min_work_elements + hw)
+        self.long_mem.add(prototype_key, prototype_value, prototype_shrinkage, selection=None, objects=None)
+
+    def consolidation(self, candidate_key, candidate_shrinkage, candidate_selection, usage, candidate_value):
+        """Pick the most-used candidates as prototypes and aggregate values into them by a dense softmax
+        readout ("potentiation", memory_manager.py:245-286)."""
+        n = candidate_key.shape[-1]
+        _, top = torch.topk(usage, k=self.num_prototypes, dim=-1, sorted=True)
+        proto = top.flatten()
+
+        # a prototype is only valid for a group whose (suffix) extent contains it
+        validity = [proto >= (n - gv.shape[2]) if gv is not None else None for gv in candidate_value]
+
+        prototype_key = candidate_key[:, :, proto]
+        prototype_selection = candidate_selection[:, :, proto] if candidate_selection is not None else None
+
+        similarity = get_similarity(candidate_key, candidate_shrinkage, prototype_key, prototype_selection)
+
+        affinity = []
+        for gi, gv in enumerate(candidate_value):
+            if gv is None:
+                affinity.append(None)
+                continue
+            sub = similarity[:, -gv.shape[2]:, validity[gi]]
+            affinity.append(do_softmax(sub) if sub.shape[-1] > 0 else None)
+
+        prototype_value = [self._readout(affinity[gi], gv) if affinity[gi] is not None else None
+                           for gi, gv in enumerate(candidate_value)]
+        prototype_shrinkage = (self._readout(affinity[0], candidate_shrinkage)
+                               if candidate_shrinkage is not None else None)
+        return prototype_key, prototype_value, prototype_shrinkage
