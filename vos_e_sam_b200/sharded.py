@@ -1,0 +1,144 @@
+"""Multi-GPU readout: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the exchange.
+
+Two ways the path shards:
+
+1. independent sequences / objects -> plain data parallelism, no collective: every rank runs its own
+   ``MemoryManager`` (``partition_sequences`` deals sequences to ranks; used by bench.py --gpus N).
+
+2. one LVOS-scale long-term bank sharded along N (``ShardedLongTermReadout``):
+     rank r owns keys [lo_r, hi_r) (packed image + fp32 keys) -> fused similarity + LOCAL top-k
+     all-gather of the (score, global index) candidates: HW * k * 12 bytes per rank
+     every rank merges the G candidate lists -> the same global top-k (vosmem_merge_topk)
+     softmax + readout of a slice of the query rows per rank from a replicated value shadow,
+     then an all-gather of the output slices (no reduction anywhere: global top-k is a subset of the
+     union of local top-k's, and the softmax needs only the k merged scores).
+   The reference has no counterpart (single GPU, tools/runner.py:32); results equal the unsharded
+   MemoryManager.match_memory by construction, which the tests check.
+
+The host logic is backend-agnostic so that the protocol is testable with gloo on CPU (tests inject a
+CPU backend built on the oracle); the product backend is ``CudaBackend`` -- kernels of libvosmem.so only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int, align: int = 64) -> Tuple[int, int]:
+    """Contiguous, tile-aligned split of [0, n) into `world` ranges; the last ranks may be empty."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def partition_sequences(n_sequences: int, world: int, rank: int) -> List[int]:
+    """Round-robin deal of independent sequences to ranks (data parallel, no collective)."""
+    return list(range(rank, n_sequences, world))
+
+
+def query_slice(hw: int, world: int, rank: int, align: int = 16) -> Tuple[int, int]:
+    per = -(-hw // world)
+    per = -(-per // align) * align
+    lo = min(hw, rank * per)
+    return lo, min(hw, lo + per)
+
+
+class CudaBackend:
+    """The product backend: every call is a libvosmem.so kernel on the current CUDA stream."""
+
+    def __init__(self, device, value_dtype=torch.bfloat16):
+        from . import ops
+        from .kv_memory_store import KeyValueMemoryStore
+        self.ops, self.device = ops, device
+        self.store_cls, self.value_dtype = KeyValueMemoryStore, value_dtype
+        self.keys = None
+        self.values = None
+
+    def load_keys(self, key, shrinkage):
+        self.keys = self.store_cls(count_usage=False, value_dtype=self.value_dtype)
+        n = key.shape[-1]
+        # the key bank carries no values of its own here (values are replicated separately)
+        self.keys.add(key.to(self.device), [], shrinkage.to(self.device), None, None)
+        return n
+
+    def load_values(self, value):
+        """value: n_obj x CV x N (full bank, replicated)."""
+        n_obj, cv, n = value.shape
+        self.values = torch.empty((n, n_obj * cv), dtype=self.value_dtype, device=self.device)
+        v = value.to(self.device).reshape(n_obj * cv, n)
+        self.ops.pack_values(v, 0, n, self.values, 0)
+        return n_obj * cv
+
+    def select(self, qk, qe, top_k, index_base):
+        n = self.keys.size
+        return self.ops.select_topk(qk, qe, [self.keys.key_segment(0, n)], top_k, index_base=index_base)
+
+    def merge(self, scores, indices):
+        return self.ops.merge_topk(scores, indices)
+
+    def readout(self, score, index, rows, n_total, out):
+        seg = self.ops.ValueSegment(shadow=self.values, first=0, count=n_total, use_count=None)
+        return self.ops.softmax_readout(score, index, [seg], rows, out=out)
+
+
+class ShardedLongTermReadout:
+    """Long-term memory bank sharded along N across `world` ranks (BASELINE.json configs[3])."""
+
+    launches_per_match = 5  # pack_query, select, merge_splits, merge_lists, softmax_readout
+
+    def __init__(self, config: dict, rank: int, world: int, device, backend=None, group=None):
+        self.top_k = config['top_k']
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.backend = backend if backend is not None else CudaBackend(device)
+        self.n_total = 0
+        self.rows = 0
+        self.lo = self.hi = 0
+
+    def load_long_term(self, key, shrinkage, value) -> None:
+        """key 1 x CK x N, shrinkage 1 x 1 x N, value n_obj x CV x N: the whole bank; this rank keeps keys [lo, hi)."""
+        self.n_total = key.shape[-1]
+        self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+        if self.hi > self.lo:
+            self.backend.load_keys(key[:, :, self.lo:self.hi], shrinkage[:, :, self.lo:self.hi])
+        self.rows = self.backend.load_values(value)
+
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
+
+    def match(self, query_key, selection, events=None) -> torch.Tensor:
+        """query_key / selection: 1 x CK x h x w  ->  rows x HW (full readout on every rank)."""
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        qk = query_key.flatten(start_dim=2)[0]
+        qe = selection.flatten(start_dim=2)[0] if selection is not None else None
+        k = self.top_k
+        if self.hi > self.lo:
+            score, index = self.backend.select(qk, qe, k, self.lo)
+        else:  # empty shard: contributes no candidates
+            score = torch.full((hw, k), float('-inf'), dtype=torch.float32, device=qk.device)
+            index = torch.full((hw, k), -1, dtype=torch.int64, device=qk.device)
+        # ---- the one exchange step: all-gather of the local top-k candidates ----
+        all_s, all_i = self._all_gather(score), self._all_gather(index)
+        g_score, g_index = self.backend.merge(all_s, all_i)            # identical on every rank
+        if events is not None:
+            events[1].record()
+        # ---- readout of this rank's slice of the query rows, then all-gather of the slices ----
+        qlo, qhi = query_slice(hw, self.world, self.rank)
+        per = query_slice(hw, self.world, 0)[1]
+        part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
+        if qhi > qlo:
+            self.backend.readout(g_score[qlo:qhi], g_index[qlo:qhi], self.rows, self.n_total, out=part[:, :qhi - qlo])
+        if events is not None:
+            events[2].record()
+        if self.world == 1:
+            return part[:, :hw]
+        gathered = self._all_gather(part)                               # world x rows x per
+        return gathered.permute(1, 0, 2).reshape(self.rows, self.world * per)[:, :hw]
