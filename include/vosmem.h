@@ -186,6 +186,8 @@ int vosmem_debug_umma_tile(const void *query_image, const void *key_image, float
 int vosmem_debug_pack_query(const float *query_key, const float *query_selection, int ck, int hw, void *image,
                             vosmem_stream_t stream);
 int64_t vosmem_query_image_bytes(int ck, int hw);
+/* per-role cycle counters of the tcgen05 kernel (16 int64 per CTA) into `device_buffer`; NULL switches it off */
+int vosmem_debug_set_timing_buffer(void *device_buffer);
 
 #ifdef __cplusplus
 }

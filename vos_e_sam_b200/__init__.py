@@ -12,9 +12,20 @@ Drop-in replacements for the reference's hot path, backed by hand-written CUDA k
 Importing the package loads the shared library and fails loudly when it has not been built
 (python -m vos_e_sam_b200.build).  There is no CPU or PyTorch fallback.
 """
-from . import _native  # noqa: F401  (loads libvosmem.so or raises)
-from .kv_memory_store import KeyValueMemoryStore
-from .memory_manager import MemoryManager
-from .memory_util import do_softmax, get_affinity, get_similarity, readout
+import importlib
 
-__all__ = ['MemoryManager', 'KeyValueMemoryStore', 'get_similarity', 'do_softmax', 'get_affinity', 'readout']
+_LAZY = {
+    'MemoryManager': 'memory_manager', 'KeyValueMemoryStore': 'kv_memory_store',
+    'get_similarity': 'memory_util', 'do_softmax': 'memory_util', 'get_affinity': 'memory_util', 'readout': 'memory_util',
+}
+__all__ = sorted(_LAZY)
+
+
+def __getattr__(name):
+    # Resolved on first use so that `vos_e_sam_b200.build` can (re)build the library before anything loads it;
+    # every one of these modules imports `_native`, which raises if libvosmem.so is missing or stale.
+    if name in _LAZY:
+        return getattr(importlib.import_module(f'{__name__}.{_LAZY[name]}'), name)
+    if name in ('ops', '_native', 'memory_manager', 'kv_memory_store', 'memory_util', 'dropin', 'sharded', 'build'):
+        return importlib.import_module(f'{__name__}.{name}')
+    raise AttributeError(f'module {__name__!r} has no attribute {name!r}')

@@ -61,6 +61,7 @@ SIGNATURES = {
     'vosmem_readout_dense': (C.c_int, [vp, i64, vp, i64, C.c_int, i64, C.c_int, vp, i64, vp]),
     'vosmem_debug_umma_tile': (C.c_int, [vp, vp, vp, vp]),
     'vosmem_debug_pack_query': (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    'vosmem_debug_set_timing_buffer': (C.c_int, [vp]),
 }
 
 

@@ -134,11 +134,12 @@ __host__ __device__ inline int image_offset(int r, int k8) {
 // Workspace carving shared by host and kernels.
 struct Workspace {
   unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
-  unsigned *tau;               // hw_pad  (order-encoded running lower bound of the k-th score)
+  float *pub;                  // splits_cap * hw_pad: r-th best score published per (split, query), -inf = none yet
   float *cand_score;           // splits * hw_pad * CAND_SLOTS
   int *cand_index;             // splits * hw_pad * CAND_SLOTS
   int *cand_count;             // splits * hw_pad
-  float *qvec;                 // SIMT path: hw * (2*ck + 1)  [-e | 2*q*e | -sum e q^2]
+  int pub_rows;                // rows of `pub` (= splits_cap)
+  float *qvec;                 // SIMT path: (2*ck + 1) x hw_pad, c-major  [-e | 2*q*e | -sum e q^2]
   int64_t bytes;
 };
 
@@ -165,7 +166,8 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
     return r;
   };
   w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
-  w.tau = reinterpret_cast<unsigned *>(take(hw_pad * 4));
+  w.pub = reinterpret_cast<float *>(take(cap * hw_pad * 4));
+  w.pub_rows = (int)cap;
   w.cand_score = reinterpret_cast<float *>(take(cap * hw_pad * CAND_SLOTS * 4));
   w.cand_index = reinterpret_cast<int *>(take(cap * hw_pad * CAND_SLOTS * 4));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));

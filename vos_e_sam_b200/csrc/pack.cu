@@ -59,37 +59,39 @@ __global__ void pack_keys_kernel(const float *__restrict__ key, int64_t key_ld, 
   store_chunk(tile, image_offset<TK>(r, 33), t);
 }
 
-// One thread per (padded) query: fp32 vector for the SIMT path, bf16 image for the tcgen05 path, and
-// the per-query threshold reset.  Image chunk order: [y1_hi | y2_hi | y1_lo | y2_lo | tail | 0] with
-// y1 = -e, y2 = 2 q e, tail = (y3_hi, y3_lo, y3_hi, 0...), y3 = -sum e q^2.
-__global__ void pack_query_kernel(const float *__restrict__ qk, const float *__restrict__ qe, int ck, int hw,
-                                  int hw_pad, float *__restrict__ qvec, unsigned char *__restrict__ image,
-                                  unsigned *__restrict__ tau) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= hw_pad) return;
-  tau[q] = ORD_NEG_INF;
+// Block = 32 queries x 8 channel groups (coalesced 128-byte reads of qk / qe).  Produces the fp32 vector for the
+// SIMT path (c-major: qvec[c * hw_pad + q]), the bf16 image for the tcgen05 path and resets the published
+// thresholds.  Image chunk order: [y1_hi | y2_hi | y1_lo | y2_lo | tail | 0] with y1 = -e, y2 = 2 q e,
+// tail = (y3_hi, y3_lo, y3_hi, 0...), y3 = -sum e q^2.
+__global__ void __launch_bounds__(256) pack_query_kernel(const float *__restrict__ qk, const float *__restrict__ qe,
+                                                         int ck, int hw, int hw_pad, int pub_rows,
+                                                         float *__restrict__ qvec, unsigned char *__restrict__ image,
+                                                         float *__restrict__ pub) {
+  __shared__ float red[8][33];
+  const int ql = threadIdx.x, gy = threadIdx.y;
+  const int q = blockIdx.x * 32 + ql;
+  for (int y = gy; y < pub_rows; y += 8) pub[(int64_t)y * hw_pad + q] = -INFINITY;
   const bool live = q < hw;
   const bool img = (ck == CK_TC);
   unsigned char *tile = image + (int64_t)(q / TQ) * QUERY_TILE_BYTES;
   const int r = q % TQ;
-  float *vec = qvec + (int64_t)q * (2 * ck + 1);
   float y3 = 0.f;
-  for (int g = 0; g < ck / 8 + (ck % 8 != 0); ++g) {
+  for (int g = gy; g * 8 < ck; g += 8) {
     Chunk8 h1, l1, h2, l2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int c = g * 8 + j;
+      const int c = g * 8 + j;
       float y1 = 0.f, y2 = 0.f;
       if (live && c < ck) {
-        float k = qk[(int64_t)c * hw + q];
-        float e = qe ? qe[(int64_t)c * hw + q] : 1.0f;
+        const float k = qk[(int64_t)c * hw + q];
+        const float e = qe ? qe[(int64_t)c * hw + q] : 1.0f;
         y1 = -e;
         y2 = 2.0f * (k * e);
         if (qe) y3 -= e * (k * k);
       }
       if (c < ck) {
-        vec[c] = y1;
-        vec[ck + c] = y2;
+        qvec[(int64_t)c * hw_pad + q] = y1;
+        qvec[(int64_t)(ck + c) * hw_pad + q] = y2;
       }
       split_bf16(y1, h1.v[j], l1.v[j]);
       split_bf16(y2, h2.v[j], l2.v[j]);
@@ -101,7 +103,12 @@ __global__ void pack_query_kernel(const float *__restrict__ qk, const float *__r
       store_chunk(tile, image_offset<TQ>(r, 24 + g), l2);
     }
   }
-  vec[2 * ck] = y3;
+  red[gy][ql] = y3;
+  __syncthreads();
+  if (gy != 0) return;
+#pragma unroll
+  for (int g = 1; g < 8; ++g) y3 += red[g][ql];
+  qvec[(int64_t)(2 * ck) * hw_pad + q] = y3;
   if (img) {
     Chunk8 t;
     __nv_bfloat16 hi, lo;
@@ -152,7 +159,7 @@ __global__ void age_kernel(float *__restrict__ life, int64_t n) {
 
 int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st) {
   int hw_pad = (int)round_up64(hw, TQ);
-  pack_query_kernel<<<(hw_pad + 127) / 128, 128, 0, st>>>(qk, qe, ck, hw, hw_pad, ws.qvec, ws.query_image, ws.tau);
+  pack_query_kernel<<<hw_pad / 32, dim3(32, 8), 0, st>>>(qk, qe, ck, hw, hw_pad, ws.pub_rows, ws.qvec, ws.query_image, ws.pub);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
@@ -207,12 +214,13 @@ extern "C" int vosmem_age(float *life_count, int64_t n, vosmem_stream_t stream) 
 extern "C" int vosmem_debug_pack_query(const float *query_key, const float *query_selection, int ck, int hw,
                                        void *image, vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(ck == CK_TC && query_key && image, "vosmem_debug_pack_query: CK must be 64, pointers non-null");
-  // image buffer layout: [query image tiles | tau (hw_pad) | qvec]; see vosmem_query_image_bytes
+  // image buffer layout: [query image tiles | one row of published thresholds (hw_pad) | qvec]; see vosmem_query_image_bytes
   Workspace ws{};
   int64_t n_qtiles = ceil_div64(hw, TQ), hw_pad = n_qtiles * TQ;
   unsigned char *p = static_cast<unsigned char *>(image);
   ws.query_image = p;
-  ws.tau = reinterpret_cast<unsigned *>(p + n_qtiles * QUERY_TILE_BYTES);
+  ws.pub = reinterpret_cast<float *>(p + n_qtiles * QUERY_TILE_BYTES);
+  ws.pub_rows = 1;
   ws.qvec = reinterpret_cast<float *>(p + n_qtiles * QUERY_TILE_BYTES + hw_pad * 4);
   return launch_pack_query(query_key, query_selection, ck, hw, ws, (cudaStream_t)stream);
 }

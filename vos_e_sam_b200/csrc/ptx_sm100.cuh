@@ -35,6 +35,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for the single-thread producer / MMA roles: back off so the spin does not steal issue slots from the
+// epilogue warp that shares the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map) -----------------------------
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
