@@ -188,6 +188,9 @@ int vosmem_debug_pack_query(const float *query_key, const float *query_selection
 int64_t vosmem_query_image_bytes(int ck, int hw);
 /* per-role cycle counters of the tcgen05 kernel (16 int64 per CTA) into `device_buffer`; NULL switches it off */
 int vosmem_debug_set_timing_buffer(void *device_buffer);
+/* cudaEvent_t handles recorded on the stream before the pack kernel and after the pack / select / last (merge, or fused
+ * merge+readout) kernel of the next vosmem_select_topk / vosmem_match calls; NULLs switch it off */
+int vosmem_debug_set_stage_events(void *begin, void *after_pack, void *after_select, void *after_last);
 
 #ifdef __cplusplus
 }

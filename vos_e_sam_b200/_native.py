@@ -62,6 +62,7 @@ SIGNATURES = {
     'vosmem_debug_umma_tile': (C.c_int, [vp, vp, vp, vp]),
     'vosmem_debug_pack_query': (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     'vosmem_debug_set_timing_buffer': (C.c_int, [vp]),
+    'vosmem_debug_set_stage_events': (C.c_int, [vp, vp, vp, vp]),
 }
 
 

@@ -8,6 +8,7 @@
 namespace vosmem {
 
 static thread_local char g_error[512] = "";
+static cudaEvent_t g_stage_events[4] = {nullptr, nullptr, nullptr, nullptr};  // begin / after pack / select / merge|readout
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -100,31 +101,67 @@ extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
   return carve_workspace(nullptr, ck, hw).bytes;
 }
 
-extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score, int64_t *out_index,
-                                  vosmem_stream_t stream) {
+// pack the query, run the selection kernel: leaves the per-split candidate lists in the workspace
+static int run_selection(const vosmem_select_desc *d, cudaStream_t st, Workspace &ws, int &splits) {
   int rc = validate_select(d);
   if (rc != VOSMEM_OK) return rc;
-  VOSMEM_CHECK_ARG(out_score && out_index, "select: null output");
-  cudaStream_t st = (cudaStream_t)stream;
-  const Workspace ws = carve_workspace(d->workspace, d->ck, d->hw);
+  ws = carve_workspace(d->workspace, d->ck, d->hw);
   int64_t total = 0;
   for (int s = 0; s < d->n_segments; ++s) total += d->seg[s].end - d->seg[s].begin;
   const int path = resolve_path(*d);
-  const int splits = choose_splits(path, d->hw, total);
+  splits = choose_splits(path, d->hw, total);
+  if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
   rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
   if (rc != VOSMEM_OK) return rc;
+  if (g_stage_events[1]) cudaEventRecord(g_stage_events[1], st);
   rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(*d, ws, splits, st) : launch_select_simt(*d, ws, splits, st);
   if (rc != VOSMEM_OK) return rc;
-  return launch_merge_splits(ws, splits, d->hw, d->top_k, d->index_base, out_score, out_index, st);
+  if (g_stage_events[2]) cudaEventRecord(g_stage_events[2], st);
+  return VOSMEM_OK;
 }
 
+extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score, int64_t *out_index,
+                                  vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(out_score && out_index, "select: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws;
+  int splits = 1;
+  int rc = run_selection(d, st, ws, splits);
+  if (rc != VOSMEM_OK) return rc;
+  rc = launch_merge_splits(ws, splits, d->hw, d->top_k, d->index_base, out_score, out_index, st);
+  if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
+  return rc;
+}
+
+namespace vosmem {
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int splits, cudaStream_t st);
+}
+
+// One object group of match_memory: pack -> select -> (merge + softmax + usage + readout in one kernel).
+// scratch_score / scratch_index are not needed by this fused path and may be NULL.
 extern "C" int vosmem_match(const vosmem_select_desc *select, const vosmem_readout_desc *readout, float *scratch_score,
                             int64_t *scratch_index, vosmem_stream_t stream) {
+  (void)scratch_score;
+  (void)scratch_index;
   VOSMEM_CHECK_ARG(select && readout, "vosmem_match: null descriptor");
   VOSMEM_CHECK_ARG(select->hw == readout->hw && select->top_k == readout->top_k,
                    "vosmem_match: select (hw=%d, k=%d) and readout (hw=%d, k=%d) disagree", select->hw, select->top_k,
                    readout->hw, readout->top_k);
-  int rc = vosmem_select_topk(select, scratch_score, scratch_index, stream);
+  VOSMEM_CHECK_ARG(select->index_base == 0, "vosmem_match: index_base must be 0 (use the staged calls for sharded banks)");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws;
+  int splits = 1;
+  int rc = run_selection(select, st, ws, splits);
   if (rc != VOSMEM_OK) return rc;
-  return vosmem_softmax_readout(readout, scratch_score, scratch_index, stream);
+  rc = launch_fused_readout(readout, ws, splits, st);
+  if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
+  return rc;
+}
+
+extern "C" int vosmem_debug_set_stage_events(void *begin, void *after_pack, void *after_select, void *after_last) {
+  g_stage_events[0] = (cudaEvent_t)begin;
+  g_stage_events[1] = (cudaEvent_t)after_pack;
+  g_stage_events[2] = (cudaEvent_t)after_select;
+  g_stage_events[3] = (cudaEvent_t)after_last;
+  return VOSMEM_OK;
 }

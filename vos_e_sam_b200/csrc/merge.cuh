@@ -1,0 +1,85 @@
+// Per-query merge of the N-split candidate lists (shared by merge_splits_kernel and the fused readout).
+#pragma once
+#include "common.cuh"
+
+namespace vosmem {
+
+constexpr int MERGE_MAX_SPLITS = 16;
+constexpr int MERGE_BUF = 128;
+
+struct SplitLists {
+  const float *cand_score;  // [splits][hw_pad][CAND_SLOTS]
+  const int *cand_index;
+  const int *cand_count;    // [splits][hw_pad]
+  const float *pub;         // [splits][hw_pad] published r-th best per (split, query); -inf = none
+  int splits, hw_pad;
+};
+
+// One warp folds the lists of query q into the exact best 32 (best first, one per lane).
+// All loads (<= MERGE_MAX_SPLITS x 64 slots per batch) are issued up front; candidates below the shared threshold
+// (min over splits of the published r-th best: a lower bound of the true 32nd best, see select_tc.cu) are dropped
+// before the sorting network sees them, which usually leaves 32-64 survivors.  buf_s / buf_i: MERGE_BUF entries of
+// warp-private shared memory.
+// MB: splits whose slots are loaded together (registers: 4 * MB per lane).
+template <int MB = MERGE_MAX_SPLITS>
+__device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, float *buf_s, int *buf_i, int lane) {
+  WarpTop32 top;
+  top.init();
+  int buffered = 0;
+  auto drain = [&]() {
+    __syncwarp();
+    for (int off = 0; off < buffered; off += 32) {
+      const bool ok = off + lane < buffered;
+      top.push(ok ? buf_s[off + lane] : -INFINITY, ok ? buf_i[off + lane] : 0x7fffffff, lane);
+    }
+    buffered = 0;
+    __syncwarp();
+  };
+  float tau = INFINITY;
+  bool tau_ready = false;
+  for (int y0 = 0; y0 < L.splits; y0 += MB) {
+    float s[MB][2];
+    int i[MB][2];
+    int my_cnt = 0;
+    if (y0 + lane < L.splits && lane < MB) my_cnt = L.cand_count[(int64_t)(y0 + lane) * L.hw_pad + q];
+#pragma unroll
+    for (int y = 0; y < MB; ++y) {
+      const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (y0 + y < L.splits) {
+          s[y][h] = L.cand_score[row + lane + 32 * h];
+          i[y][h] = L.cand_index[row + lane + 32 * h];
+        }
+      }
+    }
+    if (!tau_ready) {  // lane y owns split y
+      for (int y = lane; y < L.splits; y += 32) tau = fminf(tau, L.pub[(int64_t)y * L.hw_pad + q]);
+      tau = warp_min(tau);
+      tau_ready = true;
+    }
+#pragma unroll
+    for (int y = 0; y < MB; ++y) {
+      if (y0 + y >= L.splits) break;
+      const int cnt = __shfl_sync(FULL, my_cnt, y);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool keep = lane + 32 * h < cnt && s[y][h] >= tau && i[y][h] != 0x7fffffff;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (m == 0) continue;
+        const int add = __popc(m);
+        if (buffered + add > MERGE_BUF) drain();
+        if (keep) {
+          const int pos = buffered + __popc(m & ((1u << lane) - 1));
+          buf_s[pos] = s[y][h];
+          buf_i[pos] = i[y][h];
+        }
+        buffered += add;
+      }
+    }
+  }
+  drain();
+  return top;
+}
+
+}  // namespace vosmem

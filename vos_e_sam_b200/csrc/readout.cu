@@ -5,16 +5,22 @@
 // (tracker/inference/memory_manager.py:53-55).  Here only the k survivors are touched:
 //   out[r, q] = sum_j w[q, j] * V[index[q, j], r]
 // with V held one memory element per row (vosmem_pack_values), so each survivor is one contiguous
-// row read.  HBM/L2-bound: algorithmic bytes = rows * min(N, HW*k) * sizeof(value) + rows * HW * 4.
+// row read.  Bound by L2 -> SM gather bandwidth / latency: algorithmic bytes =
+// rows * min(N, HW*k) * sizeof(value) + rows * HW * 4 (+ the HW*k candidate list).
+//
+// Two front ends share the gather:
+//   staged : score / index lists (HW x k) come from vosmem_select_topk or a cross-rank merge;
+//   fused  : the kernel merges the per-split candidate lists of the selection kernel itself (merge.cuh), one
+//            warp per query, which removes a kernel and a round trip from vosmem_match.
 #include "common.cuh"
+#include "merge.cuh"
 
 namespace vosmem {
 
 namespace {
 
-constexpr int RQ = 16;        // queries per CTA
 constexpr int RTHREADS = 256;
-constexpr int RCH = 512;      // value rows (channels) per CTA
+constexpr int RCH = 512;      // value rows (channels) per pass
 
 struct ReadoutArgs {
   const void *shadow[2];
@@ -23,8 +29,9 @@ struct ReadoutArgs {
   float *use_count[2];
   int n_segments;
   int hw, top_k, rows;
-  const float *score;
+  const float *score;      // staged front end
   const int64_t *index;
+  SplitLists lists;        // fused front end
   float *out;
   int64_t out_ld;
   float *out_weight;
@@ -34,20 +41,24 @@ template <typename T, int VEC>
 struct Loader;
 template <>
 struct Loader<float, 4> {
-  static __device__ __forceinline__ void fma(const float *p, float w, float (&acc)[4]) {
-    float4 v = *reinterpret_cast<const float4 *>(p);
+  using Raw = float4;
+  static __device__ __forceinline__ Raw load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+  static __device__ __forceinline__ void fma(const Raw &v, float w, float (&acc)[4]) {
     acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
     acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
   }
 };
 template <>
 struct Loader<float, 1> {
-  static __device__ __forceinline__ void fma(const float *p, float w, float (&acc)[1]) { acc[0] = fmaf(w, *p, acc[0]); }
+  using Raw = float;
+  static __device__ __forceinline__ Raw load(const float *p) { return *p; }
+  static __device__ __forceinline__ void fma(const Raw &v, float w, float (&acc)[1]) { acc[0] = fmaf(w, v, acc[0]); }
 };
 template <>
 struct Loader<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void fma(const __nv_bfloat16 *p, float w, float (&acc)[8]) {
-    uint4 raw = *reinterpret_cast<const uint4 *>(p);
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+  static __device__ __forceinline__ void fma(const Raw &raw, float w, float (&acc)[8]) {
     const unsigned u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -58,40 +69,48 @@ struct Loader<__nv_bfloat16, 8> {
 };
 template <>
 struct Loader<__nv_bfloat16, 1> {
-  static __device__ __forceinline__ void fma(const __nv_bfloat16 *p, float w, float (&acc)[1]) {
-    acc[0] = fmaf(w, __bfloat162float(*p), acc[0]);
+  using Raw = __nv_bfloat16;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return *p; }
+  static __device__ __forceinline__ void fma(const Raw &v, float w, float (&acc)[1]) {
+    acc[0] = fmaf(w, __bfloat162float(v), acc[0]);
   }
 };
 
-// grid: (ceil(hw / RQ), ceil(rows / RCH)); block RTHREADS.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(RTHREADS) softmax_readout_kernel(ReadoutArgs a) {
-  constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering the channel tile
+// grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
+template <typename T, int VEC, int RQ, bool FUSED>
+__global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArgs a) {
+  constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering one pass of channels
   constexpr int GROUPS = RTHREADS / TPQ;                             // query groups working concurrently
   constexpr int CH_PER_PASS = TPQ * VEC;                             // <= RCH
   __shared__ float s_w[RQ][32];
   __shared__ const T *s_row[RQ][32];
+  __shared__ int s_any[RQ];
   __shared__ float s_out[RCH][RQ + 1];
+  __shared__ float m_s[FUSED ? RQ : 1][FUSED ? MERGE_BUF : 1];
+  __shared__ int m_i[FUSED ? RQ : 1][FUSED ? MERGE_BUF : 1];
 
   const int q0 = blockIdx.x * RQ;
-  const int ch0 = blockIdx.y * RCH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // --- softmax of the survivors, one warp per query (memory_util.py:48-49, max-subtracted) ---
+  // --- per query (one warp each): survivors -> softmax (memory_util.py:48-49, max-subtracted) -> value rows ---
   for (int qq = warp; qq < RQ; qq += RTHREADS / 32) {
     const int q = q0 + qq;
     float s = -INFINITY;
     int64_t gi = -1;
-    if (q < a.hw && lane < a.top_k) {
-      s = a.score[(int64_t)q * a.top_k + lane];
-      gi = a.index[(int64_t)q * a.top_k + lane];
-      if (gi < 0) s = -INFINITY;
+    if (q < a.hw) {
+      if (FUSED) {
+        const WarpTop32 top = merge_query<8>(a.lists, q, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane);
+        if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
+      } else if (lane < a.top_k) {
+        s = a.score[(int64_t)q * a.top_k + lane];
+        gi = a.index[(int64_t)q * a.top_k + lane];
+        if (gi < 0) s = -INFINITY;
+      }
     }
     const float m = warp_max(s);
     const float e = (s == -INFINITY) ? 0.f : expf(s - m);
     const float sum = warp_sum(e);
     float w = sum > 0.f ? e / sum : 0.f;
-    // resolve the value row
     const T *row = nullptr;
     float *use = nullptr;
 #pragma unroll
@@ -106,66 +125,87 @@ __global__ void __launch_bounds__(RTHREADS) softmax_readout_kernel(ReadoutArgs a
       if (a.out_weight) a.out_weight[(int64_t)q * a.top_k + lane] = w;
       if (use && w > 0.f) atomicAdd(use, w);  // usage = affinity row sums (memory_util.py:63)
     }
-    if (row == nullptr) {  // value lives elsewhere (another rank) or padding: contributes nothing here
-      w = 0.f;
-      row = static_cast<const T *>(a.shadow[0]);
+    // Candidates without a local value row (padding, or a value held by another rank) get weight 0 and point
+    // at a real row of the same query, so that the gather below needs no branch and never touches
+    // uninitialised memory.  A query with no local row at all is skipped.
+    const unsigned have = __ballot_sync(FULL, row != nullptr);
+    if (row == nullptr) w = 0.f;
+    if (have) {
+      const int donor = __ffs(have) - 1;
+      const unsigned long long dp = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(row), donor);
+      if (row == nullptr) row = reinterpret_cast<const T *>(dp);
     }
     s_w[qq][lane] = w;
     s_row[qq][lane] = row;
+    if (lane == 0) s_any[qq] = have != 0;
   }
   __syncthreads();
 
-  // --- gather: thread owns VEC consecutive channels of one query at a time ---
   const int g = threadIdx.x / TPQ, t = threadIdx.x % TPQ;
-  for (int cbase = 0; cbase < RCH; cbase += CH_PER_PASS) {
-    const int c_local = cbase + t * VEC;
-    const int ch = ch0 + c_local;
-    const bool ch_ok = ch < a.rows;
-    for (int qq = g; qq < RQ; qq += GROUPS) {
-      float acc[VEC];
+  for (int ch0 = blockIdx.y * RCH; ch0 < a.rows; ch0 += gridDim.y * RCH) {
+    // --- gather: thread owns VEC consecutive channels of one query at a time ---
+    for (int cbase = 0; cbase < RCH; cbase += CH_PER_PASS) {
+      const int c_local = cbase + t * VEC;
+      const int ch = ch0 + c_local;
+      const bool ch_ok = ch < a.rows;
+      for (int qq = g; qq < RQ; qq += GROUPS) {
+        float acc[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-      if (ch_ok && q0 + qq < a.hw) {
-#pragma unroll 6
-        for (int j = 0; j < a.top_k; ++j) {
-          const float w = s_w[qq][j];
-          if (w != 0.f) Loader<T, VEC>::fma(s_row[qq][j] + ch, w, acc);  // w == 0: padding / remote value
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        if (ch_ok && q0 + qq < a.hw && s_any[qq]) {
+          // eight independent row reads in flight per thread before the first use (latency-bound gather)
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            if (j0 < a.top_k) {
+              typename Loader<T, VEC>::Raw raw[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) raw[u] = Loader<T, VEC>::load(s_row[qq][j0 + u] + ch);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) Loader<T, VEC>::fma(raw[u], s_w[qq][j0 + u], acc);
+            }
+          }
         }
-      }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) s_out[c_local + v][qq] = acc[v];
+        for (int v = 0; v < VEC; ++v) s_out[c_local + v][qq] = acc[v];
+      }
     }
-  }
-  __syncthreads();
-
-  // --- write rows x HW with HW contiguous: RQ consecutive queries per row segment ---
-  for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
-    const int c_local = e / RQ, qq = e % RQ;
-    const int ch = ch0 + c_local, q = q0 + qq;
-    if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[c_local][qq];
+    __syncthreads();
+    // --- write rows x HW with HW contiguous: RQ consecutive queries per row segment ---
+    for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
+      const int c_local = e / RQ, qq = e % RQ;
+      const int ch = ch0 + c_local, q = q0 + qq;
+      if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[c_local][qq];
+    }
+    __syncthreads();
   }
 }
 
-}  // namespace
-}  // namespace vosmem
+template <int RQ, bool FUSED>
+int launch(const ReadoutArgs &a, int value_dtype, bool vec_ok, cudaStream_t st) {
+  dim3 grid((a.hw + RQ - 1) / RQ, FUSED ? 1 : (a.rows + RCH - 1) / RCH);
+  if (value_dtype == VOSMEM_F32) {
+    if (vec_ok) softmax_readout_kernel<float, 4, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+    else softmax_readout_kernel<float, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+  } else {
+    if (vec_ok) softmax_readout_kernel<__nv_bfloat16, 8, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+    else softmax_readout_kernel<__nv_bfloat16, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+  }
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
 
-using namespace vosmem;
-
-extern "C" int vosmem_softmax_readout(const vosmem_readout_desc *d, const float *score, const int64_t *index,
-                                      vosmem_stream_t stream) {
-  VOSMEM_CHECK_ARG(d && score && index, "vosmem_softmax_readout: null pointer");
-  VOSMEM_CHECK_ARG(d->hw >= 1 && d->rows >= 1 && d->out, "vosmem_softmax_readout: hw=%d rows=%d", d->hw, d->rows);
-  VOSMEM_CHECK_ARG(d->top_k >= 1 && d->top_k <= VOSMEM_MAX_TOPK, "vosmem_softmax_readout: top_k=%d outside [1, %d]",
-                   d->top_k, VOSMEM_MAX_TOPK);
-  VOSMEM_CHECK_ARG(d->n_segments >= 1 && d->n_segments <= 2, "vosmem_softmax_readout: n_segments=%d", d->n_segments);
-  VOSMEM_CHECK_ARG(d->value_dtype == VOSMEM_F32 || d->value_dtype == VOSMEM_BF16, "vosmem_softmax_readout: dtype %d",
-                   d->value_dtype);
-  ReadoutArgs a{};
-  bool vec_ok = true;
+int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
+  VOSMEM_CHECK_ARG(d != nullptr, "readout: null descriptor");
+  VOSMEM_CHECK_ARG(d->hw >= 1 && d->rows >= 1 && d->out, "readout: hw=%d rows=%d", d->hw, d->rows);
+  VOSMEM_CHECK_ARG(d->top_k >= 1 && d->top_k <= VOSMEM_MAX_TOPK, "readout: top_k=%d outside [1, %d]", d->top_k,
+                   VOSMEM_MAX_TOPK);
+  VOSMEM_CHECK_ARG(d->n_segments >= 1 && d->n_segments <= 2, "readout: n_segments=%d", d->n_segments);
+  VOSMEM_CHECK_ARG(d->value_dtype == VOSMEM_F32 || d->value_dtype == VOSMEM_BF16, "readout: dtype %d", d->value_dtype);
+  vec_ok = true;
   const int vec = d->value_dtype == VOSMEM_F32 ? 4 : 8;
   for (int s = 0; s < d->n_segments; ++s) {
     const vosmem_value_segment &g = d->seg[s];
-    VOSMEM_CHECK_ARG(g.shadow && g.shadow_ld >= d->rows && g.count >= 0, "vosmem_softmax_readout: bad value segment %d", s);
+    VOSMEM_CHECK_ARG(g.shadow && g.shadow_ld >= d->rows && g.count >= 0, "readout: bad value segment %d", s);
     a.shadow[s] = g.shadow;
     a.shadow_ld[s] = g.shadow_ld;
     a.first[s] = g.first;
@@ -178,20 +218,36 @@ extern "C" int vosmem_softmax_readout(const vosmem_readout_desc *d, const float 
   a.hw = d->hw;
   a.top_k = d->top_k;
   a.rows = d->rows;
-  a.score = score;
-  a.index = index;
   a.out = d->out;
   a.out_ld = d->out_ld;
   a.out_weight = d->out_weight;
-  dim3 grid((d->hw + RQ - 1) / RQ, (d->rows + RCH - 1) / RCH);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (d->value_dtype == VOSMEM_F32) {
-    if (vec_ok) softmax_readout_kernel<float, 4><<<grid, RTHREADS, 0, st>>>(a);
-    else softmax_readout_kernel<float, 1><<<grid, RTHREADS, 0, st>>>(a);
-  } else {
-    if (vec_ok) softmax_readout_kernel<__nv_bfloat16, 8><<<grid, RTHREADS, 0, st>>>(a);
-    else softmax_readout_kernel<__nv_bfloat16, 1><<<grid, RTHREADS, 0, st>>>(a);
-  }
-  VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
+}
+
+}  // namespace
+
+// fused front end, used by vosmem_match after the selection kernel
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int splits, cudaStream_t st) {
+  ReadoutArgs a{};
+  bool vec_ok;
+  int rc = fill_args(d, a, vec_ok);
+  if (rc != VOSMEM_OK) return rc;
+  a.lists = SplitLists{ws.cand_score, ws.cand_index, ws.cand_count, ws.pub, splits, (int)round_up64(d->hw, TQ)};
+  return launch<4, true>(a, d->value_dtype, vec_ok, st);
+}
+
+}  // namespace vosmem
+
+using namespace vosmem;
+
+extern "C" int vosmem_softmax_readout(const vosmem_readout_desc *d, const float *score, const int64_t *index,
+                                      vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(score && index, "vosmem_softmax_readout: null candidate lists");
+  ReadoutArgs a{};
+  bool vec_ok;
+  int rc = fill_args(d, a, vec_ok);
+  if (rc != VOSMEM_OK) return rc;
+  a.score = score;
+  a.index = index;
+  return launch<8, false>(a, d->value_dtype, vec_ok, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@
 // lanes stride over memory keys, the warp keeps a running best-32 (WarpTop32).  The N x HW similarity
 // matrix of the reference (memory_util.py:7-39) is never written.
 #include "common.cuh"
+#include "merge.cuh"
 
 namespace vosmem {
 
@@ -75,18 +76,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) select_simt_kernel(SimtArgs a
   if (lane == 0) a.cand_count[(int64_t)blockIdx.y * a.hw_pad + q] = 32;
 }
 
-// One warp per query: fold the per-split candidate lists into the exact top-k, best first.
-// All loads of a query (<= MERGE_MAX_SPLITS x 64 slots) are issued up front; candidates below the shared
-// threshold (min over splits of the published r-th best: a lower bound of the true 32nd best, see
-// select_tc.cu) are dropped before the sorting network sees them, which usually leaves 32-64 survivors.
-constexpr int MERGE_MAX_SPLITS = 16;
-constexpr int MERGE_BUF = 128;
-
-__global__ void __launch_bounds__(256) merge_splits_kernel(const float *__restrict__ cand_score,
-                                                           const int *__restrict__ cand_index,
-                                                           const int *__restrict__ cand_count,
-                                                           const float *__restrict__ pub, int splits, int hw,
-                                                           int hw_pad, int top_k, int64_t index_base,
+// One warp per query: fold the per-split candidate lists into the exact top-k, best first (merge.cuh).
+__global__ void __launch_bounds__(256) merge_splits_kernel(SplitLists L, int hw, int top_k, int64_t index_base,
                                                            float *__restrict__ out_score,
                                                            int64_t *__restrict__ out_index) {
   __shared__ float buf_s[8][MERGE_BUF];
@@ -94,63 +85,7 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const float *__restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   if (q >= hw) return;
-  WarpTop32 top;
-  top.init();
-  int buffered = 0;
-  auto drain = [&]() {
-    __syncwarp();
-    for (int off = 0; off < buffered; off += 32) {
-      const bool ok = off + lane < buffered;
-      top.push(ok ? buf_s[warp][off + lane] : -INFINITY, ok ? buf_i[warp][off + lane] : 0x7fffffff, lane);
-    }
-    buffered = 0;
-    __syncwarp();
-  };
-  float tau = INFINITY;
-  bool tau_ready = false;
-  for (int y0 = 0; y0 < splits; y0 += MERGE_MAX_SPLITS) {
-    // all loads of this batch first (independent), the reductions after
-    float s[MERGE_MAX_SPLITS][2];
-    int i[MERGE_MAX_SPLITS][2];
-    int my_cnt = 0;
-    if (y0 + lane < splits && lane < MERGE_MAX_SPLITS) my_cnt = cand_count[(int64_t)(y0 + lane) * hw_pad + q];
-#pragma unroll
-    for (int y = 0; y < MERGE_MAX_SPLITS; ++y) {
-      const int64_t row = ((int64_t)(y0 + y) * hw_pad + q) * CAND_SLOTS;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (y0 + y < splits) {
-          s[y][h] = cand_score[row + lane + 32 * h];
-          i[y][h] = cand_index[row + lane + 32 * h];
-        }
-      }
-    }
-    if (!tau_ready) {  // shared threshold: min over splits of the published r-th best (lane y owns split y)
-      for (int y = lane; y < splits; y += 32) tau = fminf(tau, pub[(int64_t)y * hw_pad + q]);
-      tau = warp_min(tau);
-      tau_ready = true;
-    }
-#pragma unroll
-    for (int y = 0; y < MERGE_MAX_SPLITS; ++y) {
-      if (y0 + y >= splits) break;
-      const int cnt = __shfl_sync(FULL, my_cnt, y);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const bool keep = lane + 32 * h < cnt && s[y][h] >= tau && i[y][h] != 0x7fffffff;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (m == 0) continue;
-        const int add = __popc(m);
-        if (buffered + add > MERGE_BUF) drain();
-        if (keep) {
-          const int pos = buffered + __popc(m & ((1u << lane) - 1));
-          buf_s[warp][pos] = s[y][h];
-          buf_i[warp][pos] = i[y][h];
-        }
-        buffered += add;
-      }
-    }
-  }
-  drain();
+  const WarpTop32 top = merge_query(L, q, buf_s[warp], buf_i[warp], lane);
   if (lane < top_k) {
     const bool have = top.i != 0x7fffffff;
     out_score[(int64_t)q * top_k + lane] = have ? top.s : -INFINITY;
@@ -218,8 +153,8 @@ int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int spl
 int launch_merge_splits(const Workspace &ws, int splits, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st) {
   int hw_pad = (int)round_up64(hw, TQ);
-  merge_splits_kernel<<<(hw + 7) / 8, 256, 0, st>>>(ws.cand_score, ws.cand_index, ws.cand_count, ws.pub, splits, hw,
-                                                   hw_pad, top_k, index_base, out_score, out_index);
+  SplitLists L{ws.cand_score, ws.cand_index, ws.cand_count, ws.pub, splits, hw_pad};
+  merge_splits_kernel<<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }

@@ -466,26 +466,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warp retire
     const long long t_loop = clock64() - t_begin;
 
-    // ---- hand the surviving candidates to the merge kernel (each thread writes its own list) ----
-    const int q = qtile * TQ + row;
-    if (q < a.hw) {
-      const int n = (int)((st.off_s - st.base_s) / SS);
+    // ---- hand the surviving candidates to the merge kernel: one query at a time, lanes over its entries ----
+    {
+      __syncwarp();
+      const int my_n = (int)((st.off_s - st.base_s) / SS);
       // candidate index of local index li:  64 * (g_lo + li / 64) + li % 64 + (offset of the segment)
-      const int64_t tiles0 = a.seg[0].tiles;
-      const int64_t off0 = a.seg[0].tile0 * TK - a.seg[0].begin;
-      const int64_t off1 = a.len0 + (a.seg[1].tile0 - tiles0) * TK - a.seg[1].begin;
-      const int64_t slot = ((int64_t)blockIdx.y * a.hw_pad + q) * CAND_SLOTS;
-      uint32_t rd_s = st.base_s, rd_i = st.base_i;
-      for (int e = 0; e < n; ++e) {
-        const int li = lds_u16(rd_i);
-        const int64_t g = g_lo + (li >> 6);
-        const int64_t cand = g * TK + (li & 63) + (g >= tiles0 ? off1 : off0);
-        a.cand_score[slot + e] = lds_f32(rd_s);
-        a.cand_index[slot + e] = (int)cand;
-        rd_s += SS;
-        rd_i += SI;
+      const int tiles0 = (int)a.seg[0].tiles, glo = (int)g_lo;
+      const int off0 = (int)(a.seg[0].tile0 * TK - a.seg[0].begin);
+      const int off1 = (int)(a.len0 + (a.seg[1].tile0 - a.seg[0].tiles) * TK - a.seg[1].begin);
+      const int64_t row0 = (int64_t)blockIdx.y * a.hw_pad + qtile * TQ + warp * 32;
+      if (qtile * TQ + row < a.hw) a.cand_count[row0 + lane] = my_n;
+#pragma unroll 4
+      for (int src = 0; src < 32; ++src) {
+        if (qtile * TQ + warp * 32 + src >= a.hw) break;
+        const int n = __shfl_sync(FULL, my_n, src);
+        const int srow = warp * 32 + src;
+        for (int e = lane; e < n; e += 32) {
+          const int li = ci[e * CS_H + srow];
+          const int g = glo + (li >> 6);
+          a.cand_score[(row0 + src) * CAND_SLOTS + e] = cs[e * CS_F + srow];
+          a.cand_index[(row0 + src) * CAND_SLOTS + e] = g * TK + (li & 63) + (g >= tiles0 ? off1 : off0);
+        }
       }
-      a.cand_count[(int64_t)blockIdx.y * a.hw_pad + q] = n;
     }
     if (dbg && lane == 0) {
       dbg[5 + warp * 2] = t_wait;
