@@ -70,6 +70,9 @@ def test_argument_errors_do_not_need_a_gpu(native):
     lib = native.lib
     d = native.SelectDesc()
     assert lib.vosmem_select_topk(ctypes.byref(d), None, None, None) == -22
+    assert b'null output' in lib.vosmem_last_error()
+    r = native.ReadoutDesc()
+    assert lib.vosmem_match(ctypes.byref(d), ctypes.byref(r), None, None, None) == -22
     assert b'CK' in lib.vosmem_last_error()
     assert lib.vosmem_pack_keys(None, 0, None, 32, 0, 0, None, 0, None) == -22
     assert lib.vosmem_merge_topk(None, None, 1, 1, 30, None, None, None) == -22

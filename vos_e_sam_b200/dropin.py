@@ -36,6 +36,12 @@ def install() -> None:
         if name not in _saved:
             _saved[name] = sys.modules.get(name)
         sys.modules[name] = mod
+        # `import a.b.c as x` binds getattr(a.b, 'c'), so an already-imported parent package is patched too
+        parent, _, leaf = name.rpartition('.')
+        pkg = sys.modules.get(parent)
+        if pkg is not None and hasattr(pkg, leaf):
+            _saved.setdefault((parent, leaf), getattr(pkg, leaf))
+            setattr(pkg, leaf, mod)
     for name, bindings in _CONSUMERS.items():
         mod = sys.modules.get(name)
         if mod is None:
