@@ -259,6 +259,8 @@ def run_ours(args, rank, world, local_rank):
         for i in range(K):
             step(i, events[i])
         barrier()
+        if not sharded:
+            N.lib.vosmem_debug_set_stage_events(None, None, None, None)   # the e2e calls below must not re-record them
         # ---- end-to-end through the public API with host buffers -------------------------------
         e2e_steps = K
         if not sharded:
@@ -281,8 +283,6 @@ def run_ours(args, rank, world, local_rank):
             e2e_step(i)
         barrier()
         e2e_s = time.perf_counter() - t0
-    if not sharded:
-        N.lib.vosmem_debug_set_stage_events(None, None, None, None)
     step_ms = [e[0].elapsed_time(e[4]) for e in events]
     pack_ms = [e[0].elapsed_time(e[1]) for e in events]
     sel_ms = [e[1].elapsed_time(e[2]) for e in events] if not sharded else [e[0].elapsed_time(e[1]) for e in events]

@@ -6,7 +6,9 @@ import vos_e_sam_b200 as vos
 from vos_e_sam_b200 import ops, _native as N
 from tests import synth
 g = torch.Generator().manual_seed(1)
-n, h, w = int(sys.argv[1]) if len(sys.argv) > 1 else 16200, 30, 54
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16200
+h = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+w = int(sys.argv[3]) if len(sys.argv) > 3 else 54
 k, s, _ = synth.keys(g, n)
 store = vos.KeyValueMemoryStore(False)
 store.add(k.cuda(), [], s.cuda(), None, None)

@@ -20,11 +20,12 @@
 // Thresholds.  A query's threshold is only ever a LOWER bound of its true 32nd-best score, so no true
 // top-k (k <= 32) member is dropped:
 //   local : after a cooperative cut, the (truncated) 32nd-best score of this CTA's own candidates;
-//   shared: every CTA publishes, after every tile, a lower bound of the r-th best score it has seen
-//           for the query, r = ceil(32 / splits) (tracked in registers from the maxima of the 8-column
-//           groups, which are scores of distinct keys).  The minimum over all splits has at least
-//           r * splits >= 32 keys at or above it.  With S splits running concurrently this tracks the
-//           quality of a single pass over all S ranges, which makes list overflows (and sorting) rare.
+//   shared: every thread tracks, in registers, lower bounds of the three best scores of G disjoint subsets
+//           of its CTA's keys (subset = tile index mod G; updated from the maxima of the 8-column groups,
+//           which are scores of distinct keys), G = ceil(11 / splits).  After every tile the CTA publishes
+//           the minimum over its subsets of the 3rd best; the minimum over all splits then has at least
+//           3 * G * splits >= 33 keys at or above it.  With S splits running concurrently this tracks the
+//           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -72,8 +73,7 @@ struct TcArgs {
   int64_t tiles_total;
   int hw, hw_pad, splits;
   const unsigned char *query_image;
-  float *pub;          // [splits][hw_pad] r-th best score published per (split, query)
-  int pub_rank;        // r = ceil(32 / splits)
+  float *pub;          // [splits][hw_pad] published lower bound per (split, query): see "Thresholds"
   float *cand_score;
   int *cand_index;
   int *cand_count;
@@ -150,11 +150,10 @@ __device__ __forceinline__ float shared_threshold(const float *pub_q, int splits
 //   1. pick up the latest shared threshold (warp 6 keeps it fresh in shared memory);
 //   2. every thread drops the entries of ITS list that fell below its threshold (thread-private, in place);
 //   3. lists that are still too long are cut to their best 32 by the whole warp, four queries per round
-//      (bitonic network over packed 32-bit keys), which also yields a new local threshold and, when the
-//      publishing rank is above 3, the value to publish.
+//      (bitonic network over packed 32-bit keys), which also yields a new local threshold.
 // (state goes in and comes back by value so that it stays in registers across the call)
 __device__ __noinline__ ListState relieve_lists(ListState st, float *cs, unsigned short *ci, const volatile float *tau_row,
-                                                float *pub_mine, int pub_rank, int warp, int lane) {
+                                                int warp, int lane) {
   st.tau = fmaxf(st.tau, *tau_row);
   // ---- 2. thread-private compaction ----
   {
@@ -238,13 +237,11 @@ __device__ __noinline__ ListState relieve_lists(ListState st, float *cs, unsigne
         cs[lane * CS_F + row[u]] = sv[u];
         ci[lane * CS_H + row[u]] = iv[u];
         const float floor32 = ord2f(__shfl_sync(FULL, kc[u], 31) & ~KEY_SLOT_MASK);
-        const float rth = ord2f(__shfl_sync(FULL, kc[u], (pub_rank - 1) & 31) & ~KEY_SLOT_MASK);
         if (lane == src[u]) {
           st.off_s = st.base_s + 32 * SS;
           st.off_i = st.base_i + 32 * SI;
           st.tau = fmaxf(st.tau, floor32);
         }
-        if (pub_rank > 3 && lane == 0) pub_mine[src[u]] = rth;
       }
     }
     __syncwarp();
@@ -252,6 +249,7 @@ __device__ __noinline__ ListState relieve_lists(ListState st, float *cs, unsigne
   return st;
 }
 
+template <int G>   // G = subsets of the CTA's keys whose three best scores are tracked (see "Thresholds")
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + SM_BAR);
@@ -367,9 +365,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     st.off_s = st.base_s;
     st.off_i = st.base_i;
     st.tau = -INFINITY;
-    float b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;   // lower bounds of this split's best / 2nd / 3rd score
+    float b1[G], b2[G], b3[G];   // lower bounds of the best / 2nd / 3rd score of each key subset; slot 0 = current tile's
+#pragma unroll
+    for (int u = 0; u < G; ++u) b1[u] = b2[u] = b3[u] = -INFINITY;
     float *pub_mine = a.pub + (int64_t)blockIdx.y * a.hw_pad + qtile * TQ + warp * 32;
-    const bool pub_from_regs = a.pub_rank <= 3;
     long long t_wait = 0, t_relieve = 0;
     long long t_first = 0;
     const long long t_begin = clock64();
@@ -416,16 +415,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
 #pragma unroll
         for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, __uint_as_float(v[g8 * 8 + jj]));
         gm[g8] = m;
-        const float t = fminf(b1, m);
-        b1 = fmaxf(b1, m);
-        const float u = fminf(b2, t);
-        b2 = fmaxf(b2, t);
-        b3 = fmaxf(b3, u);
+        const float t = fminf(b1[0], m);
+        b1[0] = fmaxf(b1[0], m);
+        const float u = fminf(b2[0], t);
+        b2[0] = fmaxf(b2[0], t);
+        b3[0] = fmaxf(b3[0], u);
       }
-      if (pub_from_regs) {
-        pub_mine[lane] = a.pub_rank == 1 ? b1 : (a.pub_rank == 2 ? b2 : b3);
-        if (i == 0) {
-          // First tile: nothing is known yet and all 64 scores would be kept, overflowing every list.  The
+      {
+        float pubv = b3[0];
+#pragma unroll
+        for (int u = 1; u < G; ++u) pubv = fminf(pubv, b3[u]);
+        pub_mine[lane] = pubv;
+        // rotate the subsets: the next tile updates the next one
+        const float r1 = b1[0], r2 = b2[0], r3 = b3[0];
+#pragma unroll
+        for (int u = 0; u + 1 < G; ++u) { b1[u] = b1[u + 1]; b2[u] = b2[u + 1]; b3[u] = b3[u + 1]; }
+        b1[G - 1] = r1; b2[G - 1] = r2; b3[G - 1] = r3;
+        if (G == 1 && i == 0) {
+          // First tile (single tracked subset, i.e. >= 11 splits): nothing is known yet and all 64 scores would be kept, overflowing every list.  The
           // tile sits in registers, so give the other splits a bounded moment to publish their first values
           // (the MMA warp keeps filling the other accumulator buffers meanwhile) and filter with the shared
           // threshold.  On a timeout (e.g. a grid of several waves) the lists overflow and get sorted instead.
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
           // lists that could overflow during the next 8 columns
           if (__any_sync(FULL, st.off_s > st.base_s + PRUNE_ABOVE * SS)) {
             const long long tr0 = clock64();
-            st = relieve_lists(st, cs, ci, tau_sh + row, pub_mine, a.pub_rank, warp, lane);
+            st = relieve_lists(st, cs, ci, tau_sh + row, warp, lane);
             t_relieve += clock64() - tr0;
           }
         }
@@ -584,18 +591,29 @@ int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int split
   a.splits = splits;
   a.query_image = ws.query_image;
   a.pub = ws.pub;
-  a.pub_rank = (32 + splits - 1) / splits;
   a.cand_score = ws.cand_score;
   a.cand_index = ws.cand_index;
   a.cand_count = ws.cand_count;
   a.dbg = g_tc_debug;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    attr_set = true;
-  }
   dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits);
-  select_tc_kernel<<<grid, TC_THREADS, SM_TOTAL, st>>>(a);
+  // 3 * G * splits >= 33 keys must stand behind a shared threshold
+  const int g = (11 + splits - 1) / splits;
+#define VOSMEM_LAUNCH_TC(GG)                                                                                     \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    select_tc_kernel<GG><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);                                                 \
+  } while (0)
+  if (g <= 1) VOSMEM_LAUNCH_TC(1);
+  else if (g == 2) VOSMEM_LAUNCH_TC(2);
+  else if (g == 3) VOSMEM_LAUNCH_TC(3);
+  else if (g == 4) VOSMEM_LAUNCH_TC(4);
+  else if (g <= 6) VOSMEM_LAUNCH_TC(6);
+  else VOSMEM_LAUNCH_TC(11);
+#undef VOSMEM_LAUNCH_TC
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
