@@ -63,7 +63,8 @@ def check_selection(score, index, sim64, k, what):
 
 # ------------------------------------------------------------------------------------------------
 def test_umma_tile_matches_fp32(vos):
-    """One 128 x 64 tcgen05 tile through the packed images == the fp32 similarity (descriptor / layout check)."""
+    """One 128 x 64 tcgen05 tile through the packed images (query operand staged in TMEM by tcgen05.cp, key operand
+    from shared memory) == the fp32 similarity (descriptor / layout check)."""
     g = torch.Generator().manual_seed(7)
     mk, ms, _ = synth.keys(g, 64)
     qk, qe = synth.query(g, 8, 16)

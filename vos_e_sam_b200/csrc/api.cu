@@ -27,8 +27,6 @@ int choose_splits(int path, int hw, int64_t n_total) {
     s = 148 / n_qtiles;
     int64_t by_tiles = ceil_div64(n_total, TK) / 4;
     if (s > by_tiles) s = by_tiles;
-    int64_t need = ceil_div64(ceil_div64(n_total, TK) + 2, 1024);  // 16-bit candidate index inside a CTA
-    if (s < need) s = need;
   } else {
     s = ceil_div64(4736, hw);
     int64_t by_keys = n_total / 256;
@@ -102,14 +100,16 @@ extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
 }
 
 // pack the query, run the selection kernel: leaves the per-split candidate lists in the workspace
-static int run_selection(const vosmem_select_desc *d, cudaStream_t st, Workspace &ws, int &splits) {
+static int run_selection(const vosmem_select_desc *d, cudaStream_t st, Workspace &ws, int &n_lists, int &n_pub) {
   int rc = validate_select(d);
   if (rc != VOSMEM_OK) return rc;
   ws = carve_workspace(d->workspace, d->ck, d->hw);
   int64_t total = 0;
   for (int s = 0; s < d->n_segments; ++s) total += d->seg[s].end - d->seg[s].begin;
   const int path = resolve_path(*d);
-  splits = choose_splits(path, d->hw, total);
+  const int splits = choose_splits(path, d->hw, total);
+  n_lists = splits;                                                          // candidate lists left per query
+  n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : splits;   // published threshold rows
   if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
   rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
   if (rc != VOSMEM_OK) return rc;
@@ -125,16 +125,16 @@ extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score,
   VOSMEM_CHECK_ARG(out_score && out_index, "select: null output");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
-  int splits = 1;
-  int rc = run_selection(d, st, ws, splits);
+  int n_lists = 1, n_pub = 1;
+  int rc = run_selection(d, st, ws, n_lists, n_pub);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_merge_splits(ws, splits, d->hw, d->top_k, d->index_base, out_score, out_index, st);
+  rc = launch_merge_splits(ws, n_lists, n_pub, d->hw, d->top_k, d->index_base, out_score, out_index, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }
 
 namespace vosmem {
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int splits, cudaStream_t st);
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int n_lists, int n_pub, cudaStream_t st);
 }
 
 // One object group of match_memory: pack -> select -> (merge + softmax + usage + readout in one kernel).
@@ -150,10 +150,10 @@ extern "C" int vosmem_match(const vosmem_select_desc *select, const vosmem_reado
   VOSMEM_CHECK_ARG(select->index_base == 0, "vosmem_match: index_base must be 0 (use the staged calls for sharded banks)");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
-  int splits = 1;
-  int rc = run_selection(select, st, ws, splits);
+  int n_lists = 1, n_pub = 1;
+  int rc = run_selection(select, st, ws, n_lists, n_pub);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_fused_readout(readout, ws, splits, st);
+  rc = launch_fused_readout(readout, ws, n_lists, n_pub, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }

@@ -15,8 +15,9 @@ constexpr int TQ = VOSMEM_QUERY_TILE;           // queries per image tile
 constexpr int K8 = 34;                          // 16-byte K chunks per operand row: 16 hi + 16 lo + 2 tail
 constexpr int KEY_TILE_BYTES = K8 * (TK / 8) * 128;    // 34816
 constexpr int QUERY_TILE_BYTES = K8 * (TQ / 8) * 128;  // 69632
-constexpr int CAND_SLOTS = 64;                  // per (split, query) candidate slots in the exchange buffer
+constexpr int CAND_SLOTS = 96;                  // per (split, query) candidate slots in the exchange buffer (2 x 48)
 constexpr int MAX_SPLITS = 32;
+constexpr int LISTS_PER_SPLIT = 2;              // the tcgen05 kernel publishes two thresholds per (split, query)
 
 void set_error(const char *fmt, ...);
 #define VOSMEM_CHECK_ARG(cond, ...)              \
@@ -132,13 +133,18 @@ __host__ __device__ inline int image_offset(int r, int k8) {
 
 // ------------------------------------------------------------------------------------------------
 // Workspace carving shared by host and kernels.
+struct CandEntry {   // one exchanged candidate: score + index on the candidate axis (0x7fffffff = none)
+  float score;
+  int index;
+};
+static_assert(sizeof(CandEntry) == 8, "exchange entries are read / written as 8-byte words");
+
 struct Workspace {
   unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
   float *pub;                  // splits_cap * hw_pad: r-th best score published per (split, query), -inf = none yet
-  float *cand_score;           // splits * hw_pad * CAND_SLOTS
-  int *cand_index;             // splits * hw_pad * CAND_SLOTS
+  CandEntry *cand;             // splits * hw_pad * CAND_SLOTS
   int *cand_count;             // splits * hw_pad
-  int pub_rows;                // rows of `pub` (= splits_cap)
+  int pub_rows;                // rows of `pub` (= splits_cap * LISTS_PER_SPLIT)
   float *qvec;                 // SIMT path: (2*ck + 1) x hw_pad, c-major  [-e | 2*q*e | -sum e q^2]
   int64_t bytes;
 };
@@ -155,7 +161,7 @@ inline int splits_cap(int hw) {
 
 inline Workspace carve_workspace(void *base, int ck, int hw) {
   Workspace w;
-  const int64_t cap = splits_cap(hw);
+  const int64_t cap = (int64_t)splits_cap(hw) * LISTS_PER_SPLIT;   // candidate lists per query
   int64_t n_qtiles = ceil_div64(hw, TQ);
   int64_t hw_pad = n_qtiles * TQ;
   unsigned char *p = static_cast<unsigned char *>(base);
@@ -168,8 +174,7 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
   w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
   w.pub = reinterpret_cast<float *>(take(cap * hw_pad * 4));
   w.pub_rows = (int)cap;
-  w.cand_score = reinterpret_cast<float *>(take(cap * hw_pad * CAND_SLOTS * 4));
-  w.cand_index = reinterpret_cast<int *>(take(cap * hw_pad * CAND_SLOTS * 4));
+  w.cand = reinterpret_cast<CandEntry *>(take((int64_t)splits_cap(hw) * hw_pad * CAND_SLOTS * 8));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));
   w.qvec = reinterpret_cast<float *>(take((int64_t)hw_pad * (2 * ck + 1) * 4));
   w.bytes = off;
@@ -186,7 +191,7 @@ struct SelectPlan {
 int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st);
 int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
 int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
-int launch_merge_splits(const Workspace &ws, int splits, int hw, int top_k, int64_t index_base, float *out_score,
+int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st);
 int choose_splits(int path, int hw, int64_t n_total);
 

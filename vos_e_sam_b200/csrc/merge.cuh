@@ -8,11 +8,10 @@ constexpr int MERGE_MAX_SPLITS = 16;
 constexpr int MERGE_BUF = 128;
 
 struct SplitLists {
-  const float *cand_score;  // [splits][hw_pad][CAND_SLOTS]
-  const int *cand_index;
+  const CandEntry *cand;    // [splits][hw_pad][CAND_SLOTS]
   const int *cand_count;    // [splits][hw_pad]
-  const float *pub;         // [splits][hw_pad] published r-th best per (split, query); -inf = none
-  int splits, hw_pad;
+  const float *pub;         // [pub_rows][hw_pad] published lower bounds per (virtual split, query); -inf = none
+  int splits, pub_rows, hw_pad;
 };
 
 // One warp folds the lists of query q into the exact best 32 (best first, one per lane).
@@ -20,7 +19,7 @@ struct SplitLists {
 // (min over splits of the published r-th best: a lower bound of the true 32nd best, see select_tc.cu) are dropped
 // before the sorting network sees them, which usually leaves 32-64 survivors.  buf_s / buf_i: MERGE_BUF entries of
 // warp-private shared memory.
-// MB: splits whose slots are loaded together (registers: 4 * MB per lane).
+// MB: lists whose first 32 slots are loaded together (registers: 2 * MB per lane).
 template <int MB = MERGE_MAX_SPLITS>
 __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, float *buf_s, int *buf_i, int lane) {
   WarpTop32 top;
@@ -38,43 +37,44 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
   float tau = INFINITY;
   bool tau_ready = false;
   for (int y0 = 0; y0 < L.splits; y0 += MB) {
-    float s[MB][2];
-    int i[MB][2];
+    // first 32 slots of every list of the batch + the counts, all in flight together; lists longer than 32
+    // entries (rare once the shared thresholds work) get a second, conditional read
+    CandEntry c[MB];
     int my_cnt = 0;
     if (y0 + lane < L.splits && lane < MB) my_cnt = L.cand_count[(int64_t)(y0 + lane) * L.hw_pad + q];
 #pragma unroll
     for (int y = 0; y < MB; ++y) {
-      const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (y0 + y < L.splits) {
-          s[y][h] = L.cand_score[row + lane + 32 * h];
-          i[y][h] = L.cand_index[row + lane + 32 * h];
-        }
+      if (y0 + y < L.splits) {
+        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
+        c[y] = L.cand[row + lane];
       }
     }
-    if (!tau_ready) {  // lane y owns split y
-      for (int y = lane; y < L.splits; y += 32) tau = fminf(tau, L.pub[(int64_t)y * L.hw_pad + q]);
+    if (!tau_ready) {  // lane y owns list y
+      for (int y = lane; y < L.pub_rows; y += 32) tau = fminf(tau, L.pub[(int64_t)y * L.hw_pad + q]);
       tau = warp_min(tau);
       tau_ready = true;
     }
+    auto offer = [&](bool keep, float sc, int ix) {
+      const unsigned m = __ballot_sync(FULL, keep);
+      if (m == 0) return;
+      const int add = __popc(m);
+      if (buffered + add > MERGE_BUF) drain();
+      if (keep) {
+        const int pos = buffered + __popc(m & ((1u << lane) - 1));
+        buf_s[pos] = sc;
+        buf_i[pos] = ix;
+      }
+      buffered += add;
+    };
 #pragma unroll
     for (int y = 0; y < MB; ++y) {
       if (y0 + y >= L.splits) break;
       const int cnt = __shfl_sync(FULL, my_cnt, y);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const bool keep = lane + 32 * h < cnt && s[y][h] >= tau && i[y][h] != 0x7fffffff;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (m == 0) continue;
-        const int add = __popc(m);
-        if (buffered + add > MERGE_BUF) drain();
-        if (keep) {
-          const int pos = buffered + __popc(m & ((1u << lane) - 1));
-          buf_s[pos] = s[y][h];
-          buf_i[pos] = i[y][h];
-        }
-        buffered += add;
+      offer(lane < cnt && c[y].score >= tau && c[y].index != 0x7fffffff, c[y].score, c[y].index);
+      for (int off = 32; off < cnt; off += 32) {   // rare: a list longer than 32 entries
+        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
+        const CandEntry c2 = L.cand[row + off + lane];
+        offer(off + lane < cnt && c2.score >= tau && c2.index != 0x7fffffff, c2.score, c2.index);
       }
     }
   }

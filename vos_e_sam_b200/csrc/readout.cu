@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
     int64_t gi = -1;
     if (q < a.hw) {
       if (FUSED) {
-        const WarpTop32 top = merge_query<8>(a.lists, q, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane);
+        const WarpTop32 top = merge_query<16>(a.lists, q, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane);
         if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
       } else if (lane < a.top_k) {
         s = a.score[(int64_t)q * a.top_k + lane];
@@ -227,12 +227,12 @@ int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
 }  // namespace
 
 // fused front end, used by vosmem_match after the selection kernel
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int splits, cudaStream_t st) {
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int n_lists, int n_pub, cudaStream_t st) {
   ReadoutArgs a{};
   bool vec_ok;
   int rc = fill_args(d, a, vec_ok);
   if (rc != VOSMEM_OK) return rc;
-  a.lists = SplitLists{ws.cand_score, ws.cand_index, ws.cand_count, ws.pub, splits, (int)round_up64(d->hw, TQ)};
+  a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(d->hw, TQ)};
   return launch<4, true>(a, d->value_dtype, vec_ok, st);
 }
 

@@ -23,8 +23,7 @@ struct SimtArgs {
   int ck, hw, hw_pad, splits;
   float inv_sqrt_ck;
   const float *qvec;
-  float *cand_score;
-  int *cand_index;
+  CandEntry *cand;
   int *cand_count;
 };
 
@@ -71,8 +70,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) select_simt_kernel(SimtArgs a
     top.push(score, valid ? (int)cand : 0x7fffffff, lane);
   }
   const int64_t slot = ((int64_t)blockIdx.y * a.hw_pad + q) * CAND_SLOTS;
-  a.cand_score[slot + lane] = top.s;
-  a.cand_index[slot + lane] = top.i;
+  a.cand[slot + lane] = CandEntry{top.s, top.i};
   if (lane == 0) a.cand_count[(int64_t)blockIdx.y * a.hw_pad + q] = 32;
 }
 
@@ -140,8 +138,7 @@ int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int spl
   a.splits = splits;
   a.inv_sqrt_ck = 1.0f / sqrtf((float)d.ck);
   a.qvec = ws.qvec;
-  a.cand_score = ws.cand_score;
-  a.cand_index = ws.cand_index;
+  a.cand = ws.cand;
   a.cand_count = ws.cand_count;
   dim3 grid((d.hw + SIMT_WARPS - 1) / SIMT_WARPS, splits);
   size_t smem = (size_t)SIMT_WARPS * (2 * d.ck + 1) * sizeof(float);
@@ -150,10 +147,10 @@ int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int spl
   return VOSMEM_OK;
 }
 
-int launch_merge_splits(const Workspace &ws, int splits, int hw, int top_k, int64_t index_base, float *out_score,
+int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st) {
   int hw_pad = (int)round_up64(hw, TQ);
-  SplitLists L{ws.cand_score, ws.cand_index, ws.cand_count, ws.pub, splits, hw_pad};
+  SplitLists L{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, hw_pad};
   merge_splits_kernel<<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
