@@ -163,7 +163,7 @@ def workload_config(workload, n_gpus):
         return dict(workload='davis2017_multiobject_readout', hw=DAVIS['h'] * DAVIS['w'],
                     memory_elements=DAVIS['frames'] * DAVIS['h'] * DAVIS['w'], objects=DAVIS['n_obj'], ck=CK, cv=CV,
                     top_k=TOP_K, sensory_hidden='1x5x64x30x54 held by the manager', value_storage='bf16',
-                    similarity='bf16 hi/lo split x3 -> fp32 (tcgen05)', l2='flushed before every timed step',
+                    similarity='bf16 hi/lo split x3 -> fp32 (tcgen05)', l2='flushed before every timed step', launch='one CUDA-graph replay per step',
                     parallelism=f'dp{n_gpus} (one independent sequence per GPU)')
     return dict(workload='lvos1080p_longterm_sharded_readout', hw=LVOS['h'] * LVOS['w'], memory_elements=LVOS['n_long'],
                 objects=1, ck=CK, cv=CV, top_k=TOP_K, value_storage='bf16', l2='flushed before every timed step',
@@ -250,17 +250,53 @@ def run_ours(args, rank, world, local_rank):
             e.record()          # a torch event only owns a CUDA handle once it has been recorded
         return evs
 
+    # ---- (1) headline: each step = one CUDA-graph replay of the step's kernels (no host launch gaps) ----------------
+    graphs = None
+    if not sharded:
+        N.lib.vosmem_debug_set_stage_events(None, None, None, None)
+        graphs = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for j in range(pool):
+                qk, qe = dev_q[j]
+                q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
+                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)       # warm the workspace cache outside capture
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)
+                    work.age()
+                graphs.append(gr)
+        torch.cuda.current_stream().wait_stream(side)
+
+        def run_step(i, ev):
+            flush.fill_(i & 0xFF)
+            ev[0].record()
+            graphs[i % pool].replay()
+            ev[4].record()
+    else:
+        run_step = step
+
     for i in range(W):
-        step(i, new_events())
+        run_step(i, new_events())
     barrier()
     events = [new_events() for _ in range(K)]
+    stage_events = [new_events() for _ in range(K)]
     with ClockSampler(local_rank) as clocks:
         barrier()
         for i in range(K):
-            step(i, events[i])
+            run_step(i, events[i])
         barrier()
+        # ---- (2) the same steps launched kernel by kernel with events between the kernels: per-kernel durations ----
         if not sharded:
+            for i in range(W):
+                step(i, new_events())
+            for i in range(K):
+                step(i, stage_events[i])
+            barrier()
             N.lib.vosmem_debug_set_stage_events(None, None, None, None)   # the e2e calls below must not re-record them
+        else:
+            stage_events = events
         # ---- end-to-end through the public API with host buffers -------------------------------
         e2e_steps = K
         if not sharded:
@@ -284,9 +320,10 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e2e_s = time.perf_counter() - t0
     step_ms = [e[0].elapsed_time(e[4]) for e in events]
-    pack_ms = [e[0].elapsed_time(e[1]) for e in events]
-    sel_ms = [e[1].elapsed_time(e[2]) for e in events] if not sharded else [e[0].elapsed_time(e[1]) for e in events]
-    rd_ms = [e[2].elapsed_time(e[3]) for e in events] if not sharded else [e[1].elapsed_time(e[2]) for e in events]
+    se = stage_events
+    pack_ms = [e[0].elapsed_time(e[1]) for e in se]
+    sel_ms = [e[1].elapsed_time(e[2]) for e in se] if not sharded else [e[0].elapsed_time(e[1]) for e in se]
+    rd_ms = [e[2].elapsed_time(e[3]) for e in se] if not sharded else [e[1].elapsed_time(e[2]) for e in se]
     total_ms = sum(step_ms)
 
     stats = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
@@ -331,7 +368,8 @@ def run_ours(args, rank, world, local_rank):
                 roofline_other=other, cpu_baseline=cpu,
                 stage_us=dict(pack_query=statistics.mean(pack_ms) * 1e3, select=statistics.mean(sel_ms) * 1e3,
                               readout=statistics.mean(rd_ms) * 1e3,
-                              step_median=statistics.median(step_ms) * 1e3))
+                              step_median=statistics.median(step_ms) * 1e3,
+                              step_kernel_by_kernel=statistics.median(e[0].elapsed_time(e[4]) for e in se) * 1e3))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -16,14 +16,14 @@ qk, qe = synth.query(g, h, w)
 q2, e2 = qk.cuda().flatten(2)[0], qe.cuda().flatten(2)[0]
 seg = [store.key_segment(0, n)]
 for _ in range(3): ops.select_topk(q2, e2, seg, 30, path=N.PATH_TCGEN05)
-dbg = torch.zeros(4096 * 16, dtype=torch.int64, device='cuda')
+dbg = torch.zeros(4096 * 32, dtype=torch.int64, device='cuda')
 N.lib.vosmem_debug_set_timing_buffer(dbg.data_ptr())
 ops.select_topk(q2, e2, seg, 30, path=N.PATH_TCGEN05)
 torch.cuda.synchronize()
 N.lib.vosmem_debug_set_timing_buffer(None)
-d = dbg.view(-1, 16).cpu()
+d = dbg.view(-1, 32).cpu()
 d = d[(d != 0).any(1)]
-names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total']
+names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls']
 print('CTAs', d.shape[0])
 st = d[:, 15]
 print('warp1 first-tile wait cycles: mean', float(st.float().mean()), 'max', int(st.max()))

@@ -110,6 +110,32 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                : "memory");
 }
 
+// ---- warp-convergent issue: the WHOLE warp executes these (uniform operands, so no per-instruction waterfall
+//      loop around the uniform-register operands); one elected lane issues ------------------------------------
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_cp_128x256b_elect(uint32_t tmem_dst, uint64_t smem_desc) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.cp.cta_group::1.128x256b [%0], %1;\n\t}" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive columns -----------------------------
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -76,6 +76,56 @@ struct Loader<__nv_bfloat16, 1> {
   }
 };
 
+// One warp turns query q's survivors into softmax weights and value-row pointers (32 slots; unused slots and
+// survivors without a local row get weight 0 and point at a real row of the query, so the gather needs no branch
+// on validity and never touches uninitialised memory; `any` = the query has at least one local row).
+// Also the usage scatter-add and the optional weight output (only when `side_effects`).
+template <typename T, bool FUSED>
+__device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool side_effects, float *m_s, int *m_i, int lane,
+                                              float *w_out, const T **row_out, int &any) {
+  float s = -INFINITY;
+  int64_t gi = -1;
+  if (q < a.hw) {
+    if (FUSED) {
+      const WarpTop32 top = merge_query<16>(a.lists, q, m_s, m_i, lane);
+      if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
+    } else if (lane < a.top_k) {
+      s = a.score[(int64_t)q * a.top_k + lane];
+      gi = a.index[(int64_t)q * a.top_k + lane];
+      if (gi < 0) s = -INFINITY;
+    }
+  }
+  // softmax over the survivors (memory_util.py:48-49, max-subtracted)
+  const float m = warp_max(s);
+  const float e = (s == -INFINITY) ? 0.f : expf(s - m);
+  const float sum = warp_sum(e);
+  float w = sum > 0.f ? e / sum : 0.f;
+  const T *row = nullptr;
+  float *use = nullptr;
+#pragma unroll
+  for (int sgi = 0; sgi < 2; ++sgi) {
+    if (sgi < a.n_segments && gi >= a.first[sgi] && gi < a.first[sgi] + a.count[sgi]) {
+      const int64_t r = gi - a.first[sgi];
+      row = static_cast<const T *>(a.shadow[sgi]) + r * a.shadow_ld[sgi];
+      if (a.use_count[sgi]) use = a.use_count[sgi] + r;
+    }
+  }
+  if (side_effects && q < a.hw && lane < a.top_k) {
+    if (a.out_weight) a.out_weight[(int64_t)q * a.top_k + lane] = w;
+    if (use && w > 0.f) atomicAdd(use, w);  // usage = affinity row sums (memory_util.py:63)
+  }
+  const unsigned have = __ballot_sync(FULL, row != nullptr);
+  if (row == nullptr) w = 0.f;
+  if (have) {
+    const int donor = __ffs(have) - 1;
+    const unsigned long long dp = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(row), donor);
+    if (row == nullptr) row = reinterpret_cast<const T *>(dp);
+  }
+  w_out[lane] = w;
+  row_out[lane] = row;
+  if (lane == 0) any = have != 0;
+}
+
 // grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
 template <typename T, int VEC, int RQ, bool FUSED>
 __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArgs a) {
@@ -92,53 +142,10 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
   const int q0 = blockIdx.x * RQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // --- per query (one warp each): survivors -> softmax (memory_util.py:48-49, max-subtracted) -> value rows ---
-  for (int qq = warp; qq < RQ; qq += RTHREADS / 32) {
-    const int q = q0 + qq;
-    float s = -INFINITY;
-    int64_t gi = -1;
-    if (q < a.hw) {
-      if (FUSED) {
-        const WarpTop32 top = merge_query<16>(a.lists, q, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane);
-        if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
-      } else if (lane < a.top_k) {
-        s = a.score[(int64_t)q * a.top_k + lane];
-        gi = a.index[(int64_t)q * a.top_k + lane];
-        if (gi < 0) s = -INFINITY;
-      }
-    }
-    const float m = warp_max(s);
-    const float e = (s == -INFINITY) ? 0.f : expf(s - m);
-    const float sum = warp_sum(e);
-    float w = sum > 0.f ? e / sum : 0.f;
-    const T *row = nullptr;
-    float *use = nullptr;
-#pragma unroll
-    for (int sgi = 0; sgi < 2; ++sgi) {
-      if (sgi < a.n_segments && gi >= a.first[sgi] && gi < a.first[sgi] + a.count[sgi]) {
-        const int64_t r = gi - a.first[sgi];
-        row = static_cast<const T *>(a.shadow[sgi]) + r * a.shadow_ld[sgi];
-        if (a.use_count[sgi]) use = a.use_count[sgi] + r;
-      }
-    }
-    if (blockIdx.y == 0 && q < a.hw && lane < a.top_k) {
-      if (a.out_weight) a.out_weight[(int64_t)q * a.top_k + lane] = w;
-      if (use && w > 0.f) atomicAdd(use, w);  // usage = affinity row sums (memory_util.py:63)
-    }
-    // Candidates without a local value row (padding, or a value held by another rank) get weight 0 and point
-    // at a real row of the same query, so that the gather below needs no branch and never touches
-    // uninitialised memory.  A query with no local row at all is skipped.
-    const unsigned have = __ballot_sync(FULL, row != nullptr);
-    if (row == nullptr) w = 0.f;
-    if (have) {
-      const int donor = __ffs(have) - 1;
-      const unsigned long long dp = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(row), donor);
-      if (row == nullptr) row = reinterpret_cast<const T *>(dp);
-    }
-    s_w[qq][lane] = w;
-    s_row[qq][lane] = row;
-    if (lane == 0) s_any[qq] = have != 0;
-  }
+  // --- per query (one warp each): survivors -> softmax weights -> value rows ---
+  for (int qq = warp; qq < RQ; qq += RTHREADS / 32)
+    resolve_query<T, FUSED>(a, q0 + qq, blockIdx.y == 0, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane, s_w[qq], s_row[qq],
+                            s_any[qq]);
   __syncthreads();
 
   const int g = threadIdx.x / TPQ, t = threadIdx.x % TPQ;
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
     __syncthreads();
   }
 }
+
 
 template <int RQ, bool FUSED>
 int launch(const ReadoutArgs &a, int value_dtype, bool vec_ok, cudaStream_t st) {

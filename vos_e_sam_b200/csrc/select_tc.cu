@@ -84,7 +84,7 @@ struct TcArgs {
   float *pub;          // [splits][hw_pad] published lower bound per (split, query): see "Thresholds"
   CandEntry *cand;
   int *cand_count;
-  long long *dbg;      // optional per-CTA cycle counters (16 per CTA), NULL in production
+  long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
 };
 
 // The query operand lives in tensor memory: 8 columns per K=16 step, [hi steps 0-7 | lo steps 0-7 | tail].
@@ -92,10 +92,10 @@ struct TcArgs {
 __device__ __forceinline__ void stage_query_in_tmem(uint32_t q_base, uint32_t tmem_a) {
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
-    ptx::tmem_cp_128x256b(tmem_a + 8 * s, ptx::umma_desc(q_base + (2 * s) * Q_LBO, Q_LBO, SBO));
-    ptx::tmem_cp_128x256b(tmem_a + 64 + 8 * s, ptx::umma_desc(q_base + (16 + 2 * s) * Q_LBO, Q_LBO, SBO));
+    ptx::tmem_cp_128x256b_elect(tmem_a + 8 * s, ptx::umma_desc(q_base + (2 * s) * Q_LBO, Q_LBO, SBO));
+    ptx::tmem_cp_128x256b_elect(tmem_a + 64 + 8 * s, ptx::umma_desc(q_base + (16 + 2 * s) * Q_LBO, Q_LBO, SBO));
   }
-  ptx::tmem_cp_128x256b(tmem_a + 128, ptx::umma_desc(q_base + 32 * Q_LBO, Q_LBO, SBO));
+  ptx::tmem_cp_128x256b_elect(tmem_a + 128, ptx::umma_desc(q_base + 32 * Q_LBO, Q_LBO, SBO));
 }
 // 25 MMAs of one 128 x 64 tile: hi*hi + lo*hi + hi*lo over the 128 packed channels, then the rank-1 tail.
 // Only the key operand is fetched from shared memory (2 KB per MMA), so the tensor pipe is not operand-bound.
@@ -103,12 +103,12 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_a, uint32_t k_base, uin
   const uint64_t k0 = ptx::umma_desc(k_base, K_LBO, SBO);
   constexpr uint64_t STEP = (2 * K_LBO) >> 4;   // two 8-element chunks per K=16 step, in 16-byte units
 #pragma unroll
-  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts(tmem_d, tmem_a + 8 * s, k0 + s * STEP, IDESC, s > 0);
+  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts_elect(tmem_d, tmem_a + 8 * s, k0 + s * STEP, IDESC, s > 0);
 #pragma unroll
-  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts(tmem_d, tmem_a + 64 + 8 * s, k0 + s * STEP, IDESC, 1);
+  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts_elect(tmem_d, tmem_a + 64 + 8 * s, k0 + s * STEP, IDESC, 1);
 #pragma unroll
-  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts(tmem_d, tmem_a + 8 * s, k0 + (8 + s) * STEP, IDESC, 1);
-  ptx::umma_bf16_ts(tmem_d, tmem_a + 128, k0 + 16 * STEP, IDESC, 1);
+  for (int s = 0; s < 8; ++s) ptx::umma_bf16_ts_elect(tmem_d, tmem_a + 8 * s, k0 + (8 + s) * STEP, IDESC, 1);
+  ptx::umma_bf16_ts_elect(tmem_d, tmem_a + 128, k0 + 16 * STEP, IDESC, 1);
 }
 
 struct ListState {
@@ -151,24 +151,28 @@ __device__ __forceinline__ float shared_threshold(const float *pub_q, int splits
 //   2. every thread drops the entries of ITS list that fell below its threshold (thread-private, in place);
 //   3. lists that are still too long are cut to their best 32 by the whole warp, four queries per round
 //      (bitonic network over packed 32-bit keys), which also yields a new local threshold.
+// Every thread drops the entries of its own list that are below its threshold (in place, order kept).
+__device__ __forceinline__ ListState compact_list(ListState st) {
+  const int cnt = (int)((st.off - st.base) / SS);
+  const int nmax = __reduce_max_sync(FULL, cnt);
+  uint32_t rd = st.base, wr = st.base;
+  for (int e = 0; e < nmax; ++e) {
+    const bool in = rd < st.off;
+    Entry en = lds_entry(in ? rd : st.base);
+    if (!in) en.score = __int_as_float(0x7fc00000);  // NaN never passes the compare
+    VOSMEM_APPEND("ge", wr, en.score, st.tau, en.index);
+    rd += SS;
+  }
+  st.off = wr;
+  return st;
+}
+
 // (state goes in and comes back by value so that it stays in registers across the call)
 __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const volatile float *tau_row, int quarter,
                                                 int lane) {
   st.tau = fmaxf(st.tau, *tau_row);
   // ---- 2. thread-private compaction ----
-  {
-    const int cnt = (int)((st.off - st.base) / SS);
-    const int nmax = __reduce_max_sync(FULL, cnt);
-    uint32_t rd = st.base, wr = st.base;
-    for (int e = 0; e < nmax; ++e) {
-      const bool in = rd < st.off;
-      Entry en = lds_entry(in ? rd : st.base);
-      if (!in) en.score = __int_as_float(0x7fc00000);  // NaN never passes the compare
-      VOSMEM_APPEND("ge", wr, en.score, st.tau, en.index);
-      rd += SS;
-    }
-    st.off = wr;
-  }
+  st = compact_list(st);
   // ---- 3. cooperative cut to the best 32 ----
   unsigned full = __ballot_sync(FULL, st.off > st.base + PRUNE_ABOVE * SS);
   while (full) {
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
   const int64_t g_lo = a.tiles_total * blockIdx.y / a.splits;
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
   const int n_tiles = (int)(g_hi - g_lo);
-  long long *dbg = a.dbg ? a.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+  long long *dbg = a.dbg ? a.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_empty + i, 1); }
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(FULL, *tmem_slot, 0);   // provably warp-uniform
 
   if (warp == W_REFRESH) {
     // ===== threshold refresher: tau_sh[row] = min over the virtual splits of their published lower bound =====
@@ -326,13 +330,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       if (dbg) dbg[0] = t_wait;
     }
   } else if (warp == W_MMA) {
-    // ===== MMA issuer =====
-    if (lane == 0 && n_tiles > 0) {
+    // ===== MMA issuer: the whole warp runs the loop in lock step (every operand is warp-uniform by construction, so
+    //       the uniform-register operands of UTCHMMA need no per-instruction waterfall loop); one elected lane issues
+    if (n_tiles > 0) {
       const uint32_t tmem_a = tmem_base + TMEM_A;
       ptx::mbar_wait(bar_q, 0);
       ptx::tc_fence_after();
       stage_query_in_tmem(ptx::smem_u32(smem + SM_Q), tmem_a);
-      ptx::umma_commit(bar_qdone);   // arrives once the copies have read shared memory
+      ptx::umma_commit_elect(bar_qdone);   // arrives once the copies have read shared memory
       long long t_acc = 0, t_ld = 0, t_issue = 0;
       const long long t_begin = clock64();
       for (int i = 0; i < n_tiles; ++i) {
@@ -346,11 +351,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
         t_ld += t2 - t1;
         ptx::tc_fence_after();
         issue_tile(tmem_a, ptx::smem_u32(smem + SM_K + st * KEY_TILE_BYTES), tmem_base + buf * TK);
-        ptx::umma_commit(bar_empty + st);   // key stage reusable once these MMAs have read it
-        ptx::umma_commit(bar_tfull + buf);  // accumulator ready for the epilogue
+        ptx::umma_commit_elect(bar_empty + st);   // key stage reusable once these MMAs have read it
+        ptx::umma_commit_elect(bar_tfull + buf);  // accumulator ready for the epilogue
         t_issue += clock64() - t2;
       }
-      if (dbg) { dbg[1] = t_acc; dbg[2] = t_ld; dbg[3] = t_issue; dbg[4] = clock64() - t_begin; }
+      if (dbg && lane == 0) { dbg[1] = t_acc; dbg[2] = t_ld; dbg[3] = t_issue; dbg[4] = clock64() - t_begin; }
     }
   } else {
     // ===== epilogue: warps 0-7; warp w owns TMEM lanes 32*(w%4).. and drains the tiles with i % 2 == w/4 =====
@@ -367,7 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
 #pragma unroll
     for (int u = 0; u < G; ++u) b1[u] = b2[u] = b3[u] = -INFINITY;
     float *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
-    long long t_wait = 0, t_relieve = 0, t_first = 0;
+    long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
+    int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
     const long long t_begin = clock64();
     for (int i = half; i < n_tiles; i += HALVES) {
@@ -389,6 +395,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + buf);  // accumulator buffer free again
+      const long long tp1 = clock64();
+      t_ld += tp1 - tw0;
       st.tau = fmaxf(st.tau, tau_sh[row]);
 
       // first / last tile of a candidate range: columns outside it never qualify
@@ -448,6 +456,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
 #pragma unroll
       for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] > st.tau ? 1u : 0u) << g8;
       const unsigned active = __reduce_or_sync(FULL, mine);
+      const long long tp2 = clock64();
+      t_max += tp2 - tp1;
+      n_active += __popc(active);
 
       const uint32_t li0 = (uint32_t)i * TK;
 #pragma unroll
@@ -467,11 +478,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
               const long long tr0 = clock64();
               st = relieve_lists(st, cs, tau_sh + row, quarter, lane);
               t_relieve += clock64() - tr0;
+              ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
             }
           }
         }
       }
+      t_app += clock64() - tp2;
     }
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warp retire
@@ -480,6 +493,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     // ---- hand the surviving candidates to the merge: both sets of a query share one exchange row, set 0 first.
     //      Lanes run over the entries of a row (coalesced 8-byte stores), four rows per step for ILP. ----
     {
+      // last look at the shared threshold: what the other splits found meanwhile shortens the hand-off (and the merge)
+      st.tau = fmaxf(st.tau, tau_sh[row]);
+      st = compact_list(st);
       const int my_n = (int)((st.off - st.base) / SS);
       if (half == 0) n_set0[row] = my_n;
       // the two warps of a lane quarter meet here (named barrier 1 + quarter, 64 threads)
@@ -517,6 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       dbg[6 + quarter * 2] = t_relieve;
       if (quarter == 0) { dbg[13] = t_loop; dbg[14] = clock64() - t_begin; }
       if (quarter == 1) dbg[15] = t_first;
+      if (quarter == 0) { dbg[16] = t_ld; dbg[17] = t_max; dbg[18] = t_app; dbg[19] = n_active; dbg[20] = n_relieve; }
     }
   }
 
@@ -552,12 +569,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_tile_kernel(const unsigned
     ptx::bulk_g2s(smem + SM_Q, query_image, QUERY_TILE_BYTES / 2, bar_ld);
     ptx::bulk_g2s(smem + SM_Q + QUERY_TILE_BYTES / 2, query_image + QUERY_TILE_BYTES / 2, QUERY_TILE_BYTES / 2, bar_ld);
     ptx::bulk_g2s(smem + SM_K + 2 * KEY_TILE_BYTES, key_image, KEY_TILE_BYTES, bar_ld);
-  } else if (warp == W_MMA && lane == 0) {
+  } else if (warp == W_MMA) {
     ptx::mbar_wait(bar_ld, 0);
     ptx::tc_fence_after();
     stage_query_in_tmem(ptx::smem_u32(smem + SM_Q), tmem_base + TMEM_A);
     issue_tile(tmem_base + TMEM_A, ptx::smem_u32(smem + SM_K + 2 * KEY_TILE_BYTES), tmem_base);
-    ptx::umma_commit(bar_mma);
+    ptx::umma_commit_elect(bar_mma);
   } else if (warp < 4) {
     ptx::mbar_wait(bar_mma, 0);
     ptx::tc_fence_after();
