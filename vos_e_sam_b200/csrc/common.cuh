@@ -15,7 +15,7 @@ constexpr int TQ = VOSMEM_QUERY_TILE;           // queries per image tile
 constexpr int K8 = 34;                          // 16-byte K chunks per operand row: 16 hi + 16 lo + 2 tail
 constexpr int KEY_TILE_BYTES = K8 * (TK / 8) * 128;    // 34816
 constexpr int QUERY_TILE_BYTES = K8 * (TQ / 8) * 128;  // 69632
-constexpr int CAND_SLOTS = 96;                  // per (split, query) candidate slots in the exchange buffer (2 x 48)
+constexpr int CAND_SLOTS = 120;                 // per (split, query) candidate slots in the exchange buffer (2 x 60)
 constexpr int MAX_SPLITS = 32;
 constexpr int LISTS_PER_SPLIT = 2;              // the tcgen05 kernel publishes two thresholds per (split, query)
 

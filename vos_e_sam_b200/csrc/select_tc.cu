@@ -24,12 +24,13 @@
 // Thresholds.  A query's threshold is only ever a LOWER bound of its true 32nd-best score, so no true
 // top-k (k <= 32) member is dropped:
 //   local : after a cooperative cut, the (truncated) 32nd-best score of this CTA's own candidates;
-//   shared: every thread tracks, in registers, lower bounds of the three best scores of G disjoint subsets
-//           of its CTA's keys (subset = tile index mod G; updated from the maxima of the 8-column groups,
-//           which are scores of distinct keys), G = ceil(11 / splits).  After every tile the CTA publishes
-//           the minimum over its subsets of the 3rd best; the minimum over all splits then has at least
-//           3 * G * splits >= 33 keys at or above it.  With S splits running concurrently this tracks the
-//           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
+//   shared: every thread tracks, in registers, lower bounds of the R best scores of the keys its warp set has seen
+//           (a sorted insertion of the maxima of the 8-column groups during the first tiles, of the tile maximum
+//           afterwards: maxima of disjoint column sets are scores of distinct keys), R = ceil(33 / virtual splits),
+//           and publishes the R-th after every tile; every cooperative cut also publishes the exact R-th best of
+//           the list it sorted.  The minimum over all virtual splits then has at least 33 keys at or above it.
+//           With S splits running concurrently this tracks the quality of a single pass over all keys, which makes
+//           list overflows (and sorting) rare.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -44,16 +45,19 @@ constexpr int HALVES = 2;                 // epilogue warp sets = virtual splits
 constexpr int EPI_WARPS = 4 * HALVES;
 constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_REFRESH = EPI_WARPS + 2;
 constexpr int TC_THREADS = (EPI_WARPS + 3) * 32;   // 352
-constexpr int CSLOTS = 48;             // candidate slots per (virtual split, query) in shared memory
+constexpr int CSLOTS = 60;             // candidate slots per (virtual split, query) in shared memory
 constexpr int CS_E = TQ + 1;           // 8-byte {score, local index} entries per slot row (+1: bank spread)
-constexpr int PRUNE_ABOVE = CSLOTS - 8;
+constexpr int PRUNE_ABOVE = CSLOTS - 8;     // a list this long may overflow during the next 8 columns: relieve the warp
+constexpr int SORT_ABOVE = CSLOTS - 16;     // lists still longer than this after the compaction are cut to their best 32
 constexpr uint32_t SS = CS_E * 8;      // byte stride between consecutive slots of one list
 constexpr uint32_t KEY_SLOT_MASK = 63u;           // low bits of a sort key hold the slot id
-constexpr int FIRST_WAIT_CYCLES = 20000;          // bounded wait for the other splits' first publication
+constexpr int FIRST_WAIT_CYCLES = 20000;
+constexpr int TRACK_TILES = 16;                   // tiles per warp set during which the subsets' best scores are tracked          // bounded wait for the other splits' first publication
 
 // shared memory map (bytes)
 constexpr int SM_K = 0;                                 // key stages; the first two also stage the query image once
 constexpr int SM_Q = SM_K;
+static_assert(CSLOTS <= 64 && 2 * CSLOTS <= CAND_SLOTS, "list length vs sort width / exchange row");
 static_assert(2 * KEY_TILE_BYTES == QUERY_TILE_BYTES && STAGES >= 2, "query image must fit the first two stages");
 constexpr int LIST_BYTES = CSLOTS * CS_E * 8;
 constexpr int SM_CS = SM_K + STAGES * KEY_TILE_BYTES;   // HALVES candidate lists
@@ -115,6 +119,7 @@ struct ListState {
   uint32_t base;   // shared-memory byte address of slot 0 of this thread's list
   uint32_t off;    // next free slot
   float tau;       // current threshold (lower bound of this query's true 32nd-best score)
+  float pub;       // lower bound of the `rank`-th best score of this list's keys that this thread has published
 };
 struct Entry {
   float score;
@@ -169,12 +174,12 @@ __device__ __forceinline__ ListState compact_list(ListState st) {
 
 // (state goes in and comes back by value so that it stays in registers across the call)
 __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const volatile float *tau_row, int quarter,
-                                                int lane) {
+                                                int lane, int rank) {
   st.tau = fmaxf(st.tau, *tau_row);
   // ---- 2. thread-private compaction ----
   st = compact_list(st);
   // ---- 3. cooperative cut to the best 32 ----
-  unsigned full = __ballot_sync(FULL, st.off > st.base + PRUNE_ABOVE * SS);
+  unsigned full = __ballot_sync(FULL, st.off > st.base + SORT_ABOVE * SS);
   while (full) {
     int src[4];
     bool on[4];
@@ -233,9 +238,11 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
       if (on[u]) {
         cs[lane * CS_E + row[u]] = sv[u];
         const float floor32 = ord2f(__shfl_sync(FULL, kc[u], 31) & ~KEY_SLOT_MASK);
+        const float at_rank = ord2f(__shfl_sync(FULL, kc[u], rank - 1) & ~KEY_SLOT_MASK);   // exact (truncated) rank-th best
         if (lane == src[u]) {
           st.off = st.base + 32 * SS;
           st.tau = fmaxf(st.tau, floor32);
+          st.pub = fmaxf(st.pub, at_rank);
         }
       }
     }
@@ -244,7 +251,7 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
   return st;
 }
 
-template <int G>   // G = subsets of a virtual split's keys whose three best scores are tracked (see "Thresholds")
+template <int R>   // R = tracked / published rank per virtual split (see "Thresholds")
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + SM_BAR);
@@ -368,13 +375,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     st.base = ptx::smem_u32(cs) + row * 8;
     st.off = st.base;
     st.tau = -INFINITY;
-    float b1[G], b2[G], b3[G];   // lower bounds of the best / 2nd / 3rd score of each key subset; slot 0 = current tile's
+    st.pub = -INFINITY;
+    float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
 #pragma unroll
-    for (int u = 0; u < G; ++u) b1[u] = b2[u] = b3[u] = -INFINITY;
+    for (int u = 0; u < R; ++u) best[u] = -INFINITY;
     float *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
     long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
     int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
+    const int track_end = half + HALVES * TRACK_TILES;   // group maxima feed the tracker up to here, tile maxima after
+    // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
+    const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
+              edge3 = (int)(a.tiles_total - 1 - g_lo);
     const long long t_begin = clock64();
     for (int i = half; i < n_tiles; i += HALVES) {
       const int buf = i % ACC_BUFS;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       st.tau = fmaxf(st.tau, tau_sh[row]);
 
       // first / last tile of a candidate range: columns outside it never qualify
-      {
+      if (i == edge0 || i == edge1 || i == edge2 || i == edge3) {
         const int64_t g = g_lo + i;
         const int sg = g >= a.seg[0].tiles;
         const int64_t key0 = (sg ? a.seg[1].tile0 + (g - a.seg[0].tiles) : a.seg[0].tile0 + g) * TK;
@@ -412,8 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
             if (j < jlo || j >= jhi) v[j] = 0xff800000u;  // -inf
         }
       }
-      // maxima of the 8-column groups: (a) which groups hold a survivor for any lane, (b) running lower bounds of
-      // the three best scores of this tile's key subset (group maxima are scores of distinct keys)
+      // maxima of the 8-column groups: which groups hold a survivor for any lane
       float gm[TK / 8];
 #pragma unroll
       for (int g8 = 0; g8 < TK / 8; ++g8) {
@@ -421,36 +432,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
 #pragma unroll
         for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, __uint_as_float(v[g8 * 8 + jj]));
         gm[g8] = m;
-        const float t = fminf(b1[0], m);
-        b1[0] = fmaxf(b1[0], m);
-        const float u = fminf(b2[0], t);
-        b2[0] = fmaxf(b2[0], t);
-        b3[0] = fmaxf(b3[0], u);
       }
-      {
-        float pubv = b3[0];
+      auto track = [&](float m) {   // sorted insertion, 2 R - 1 min / max
 #pragma unroll
-        for (int u = 1; u < G; ++u) pubv = fminf(pubv, b3[u]);
-        pub_mine[lane] = pubv;
-        // rotate the subsets: the next tile updates the next one
-        const float r1 = b1[0], r2 = b2[0], r3 = b3[0];
-#pragma unroll
-        for (int u = 0; u + 1 < G; ++u) { b1[u] = b1[u + 1]; b2[u] = b2[u + 1]; b3[u] = b3[u + 1]; }
-        b1[G - 1] = r1; b2[G - 1] = r2; b3[G - 1] = r3;
-        if (G == 1 && i == half) {
-          // First tile of this set (single tracked subset, i.e. >= 6 splits): nothing is known yet and every score
-          // would be kept.  The tile sits in registers, so give the other splits a bounded moment to publish their
-          // first values (the MMA warp keeps filling the other accumulator buffers meanwhile) and filter with the
-          // shared threshold.  On a timeout (e.g. a grid of several waves) the lists overflow and get sorted instead.
-          const long long t0 = clock64();
-          float shared = tau_sh[row];
-          while (__any_sync(FULL, shared == -INFINITY) && clock64() - t0 < FIRST_WAIT_CYCLES) {
-            __nanosleep(100);
-            shared = tau_sh[row];
-          }
-          st.tau = fmaxf(st.tau, shared);
-          t_first = clock64() - t0;
+        for (int u = 0; u < R; ++u) {
+          const float lo = fminf(best[u], m);
+          best[u] = fmaxf(best[u], m);
+          m = lo;
         }
+      };
+      if (i < track_end) {
+#pragma unroll
+        for (int g8 = 0; g8 < TK / 8; ++g8) track(gm[g8]);
+      } else {
+        float tm = gm[0];
+#pragma unroll
+        for (int g8 = 1; g8 < TK / 8; ++g8) tm = fmaxf(tm, gm[g8]);
+        track(tm);
+      }
+      if (best[R - 1] > st.pub) {
+        st.pub = best[R - 1];
+        pub_mine[lane] = st.pub;
+      }
+      if (R <= 3 && i == half) {
+        // First tile of this set with many splits: nothing is known yet and every score would be kept.  The tile
+        // sits in registers, so give the other splits a bounded moment to publish their first values (the MMA warp
+        // keeps filling the other accumulator buffers meanwhile) and filter with the shared threshold.  On a
+        // timeout (e.g. a grid of several waves) the lists overflow and get sorted instead.
+        const long long t0 = clock64();
+        float shared = tau_sh[row];
+        while (__any_sync(FULL, shared == -INFINITY) && clock64() - t0 < FIRST_WAIT_CYCLES) {
+          __nanosleep(100);
+          shared = tau_sh[row];
+        }
+        st.tau = fmaxf(st.tau, shared);
+        t_first = clock64() - t0;
       }
       unsigned mine = 0;
 #pragma unroll
@@ -458,12 +474,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       const unsigned active = __reduce_or_sync(FULL, mine);
       const long long tp2 = clock64();
       t_max += tp2 - tp1;
-      n_active += __popc(active);
 
       const uint32_t li0 = (uint32_t)i * TK;
 #pragma unroll
       for (int g8 = 0; g8 < TK / 8; ++g8) {
         if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
+          ++n_active;
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int j = g8 * 8 + jj;
@@ -476,7 +492,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
             len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
             if (len_bound > PRUNE_ABOVE) {
               const long long tr0 = clock64();
-              st = relieve_lists(st, cs, tau_sh + row, quarter, lane);
+              const float pub_before = st.pub;
+              st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
+              if (st.pub > pub_before) pub_mine[lane] = st.pub;
               t_relieve += clock64() - tr0;
               ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
@@ -627,23 +645,24 @@ int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int split
   a.cand_count = ws.cand_count;
   a.dbg = g_tc_debug;
   dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits);
-  // 3 * G * (virtual splits) >= 33 keys must stand behind a shared threshold
-  const int g = (11 + HALVES * splits - 1) / (HALVES * splits);
-#define VOSMEM_LAUNCH_TC(GG)                                                                                     \
+  // R * (virtual splits) >= 33 keys must stand behind a shared threshold
+  const int r = (33 + HALVES * splits - 1) / (HALVES * splits);
+#define VOSMEM_LAUNCH_TC(RR)                                                                                     \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
     if (!attr_set) {                                                                                             \
-      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    select_tc_kernel<GG><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);                                                 \
+    select_tc_kernel<RR><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);                                                 \
   } while (0)
-  if (g <= 1) VOSMEM_LAUNCH_TC(1);
-  else if (g == 2) VOSMEM_LAUNCH_TC(2);
-  else if (g == 3) VOSMEM_LAUNCH_TC(3);
-  else if (g == 4) VOSMEM_LAUNCH_TC(4);
-  else if (g <= 6) VOSMEM_LAUNCH_TC(6);
-  else VOSMEM_LAUNCH_TC(11);
+  if (r <= 1) VOSMEM_LAUNCH_TC(1);
+  else if (r == 2) VOSMEM_LAUNCH_TC(2);
+  else if (r == 3) VOSMEM_LAUNCH_TC(3);
+  else if (r == 4) VOSMEM_LAUNCH_TC(4);
+  else if (r <= 6) VOSMEM_LAUNCH_TC(6);
+  else if (r <= 9) VOSMEM_LAUNCH_TC(9);
+  else VOSMEM_LAUNCH_TC(17);
 #undef VOSMEM_LAUNCH_TC
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
