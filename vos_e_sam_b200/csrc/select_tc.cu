@@ -38,8 +38,8 @@ namespace vosmem {
 namespace {
 
 constexpr int STAGES = 3;
-constexpr int ACC_BUFS = 4;
-constexpr int TMEM_COLS = 512;            // 4 accumulator buffers (256 columns) + the query operand (136 columns)
+constexpr int ACC_BUFS = 5;
+constexpr int TMEM_COLS = 512;            // 5 accumulator buffers (320 columns) + the query operand (136 columns)
 constexpr int TMEM_A = ACC_BUFS * TK;     // first column of the query operand: [hi 64 | lo 64 | tail 8]
 constexpr int HALVES = 2;                 // epilogue warp sets = virtual splits per CTA (set s drains tiles i % 2 == s)
 constexpr int EPI_WARPS = 4 * HALVES;
@@ -66,7 +66,8 @@ constexpr int N_BARS = 2 * STAGES + 2 * ACC_BUFS + 2;
 constexpr int SM_TMEM = SM_BAR + N_BARS * 8;   // [0] TMEM base address, [1] epilogue warps finished
 constexpr int SM_TAU = SM_TMEM + 16;           // TQ floats: shared threshold per query row, kept fresh by the refresher
 constexpr int SM_NA = SM_TAU + TQ * 4;         // TQ ints: list length of warp set 0 per query row (for the hand-off)
-constexpr int SM_TOTAL = SM_NA + TQ * 4;
+constexpr int SM_CTR = SM_NA + TQ * 4;          // 4 ints: next tile of each TMEM lane quarter (dynamic hand-out to its two warps)
+constexpr int SM_TOTAL = SM_CTR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget exceeded");
 
 constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TQ, TK);
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     ptx::mbar_init(bar_qdone, 1);
     ptx::fence_barrier_init();
     *epi_done = 0;
+    for (int i = 0; i < 4; ++i) reinterpret_cast<int *>(smem + SM_CTR)[i] = 0;
   }
   if (threadIdx.x < TQ) tau_sh[threadIdx.x] = -INFINITY;
   if (warp == W_MMA) {
@@ -383,12 +385,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
     int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
-    const int track_end = half + HALVES * TRACK_TILES;   // group maxima feed the tracker up to here, tile maxima after
+    // Tiles are handed out dynamically to the two warps of a lane quarter (shared-memory counter), so a warp that is
+    // busy cutting its lists does not hold up the accumulator ring: its partner drains the tiles meanwhile.  Lists,
+    // thresholds and the tracker are per warp set and do not care which tiles they see.
+    int *tile_ctr = reinterpret_cast<int *>(smem + SM_CTR) + quarter;
+    int n_done = 0;      // tiles this warp has drained
+    int grabbed = 0;     // lane 0: the next tile of this warp (fetched one iteration ahead to hide the atomic)
+    if (lane == 0) grabbed = atomicAdd(tile_ctr, 1);
     // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
     const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
               edge3 = (int)(a.tiles_total - 1 - g_lo);
     const long long t_begin = clock64();
-    for (int i = half; i < n_tiles; i += HALVES) {
+    for (int i = __shfl_sync(FULL, grabbed, 0); i < n_tiles; i = __shfl_sync(FULL, grabbed, 0), ++n_done) {
       const int buf = i % ACC_BUFS;
       const long long tw0 = clock64();
       ptx::mbar_wait(bar_tfull + buf, (i / ACC_BUFS) & 1);
@@ -406,7 +414,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + buf);  // accumulator buffer free again
+      if (lane == 0) {
+        ptx::mbar_arrive(bar_tempty + buf);  // accumulator buffer free again
+        grabbed = atomicAdd(tile_ctr, 1);
+      }
       const long long tp1 = clock64();
       t_ld += tp1 - tw0;
       st.tau = fmaxf(st.tau, tau_sh[row]);
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
           m = lo;
         }
       };
-      if (i < track_end) {
+      if (n_done < TRACK_TILES) {   // group maxima feed the tracker during the first tiles, tile maxima after
 #pragma unroll
         for (int g8 = 0; g8 < TK / 8; ++g8) track(gm[g8]);
       } else {
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
         st.pub = best[R - 1];
         pub_mine[lane] = st.pub;
       }
-      if (R <= 3 && i == half) {
+      if (R <= 3 && n_done == 0) {
         // First tile of this set with many splits: nothing is known yet and every score would be kept.  The tile
         // sits in registers, so give the other splits a bounded moment to publish their first values (the MMA warp
         // keeps filling the other accumulator buffers meanwhile) and filter with the shared threshold.  On a
@@ -480,11 +491,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       for (int g8 = 0; g8 < TK / 8; ++g8) {
         if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
           ++n_active;
+          // slot addresses first (one select + add per column, each in a fresh register), then the predicated
+          // stores: no store waits for the previous store to release its address register
+          uint32_t slot[9];
+          slot[0] = st.off;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) > st.tau ? SS : 0u);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int j = g8 * 8 + jj;
-            VOSMEM_APPEND("gt", st.off, __uint_as_float(v[j]), st.tau, li0 + j);
+            if (__uint_as_float(v[j]) > st.tau)
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot[jj]), "r"(v[j]), "r"(li0 + j) : "memory");
           }
+          st.off = slot[8];
           // Lists that could overflow during the next 8 columns.  The warp-uniform bound makes the real (voted) check
           // rare: lists are short once the shared thresholds work.
           len_bound += 8;
