@@ -14,6 +14,18 @@ struct SplitLists {
   int splits, pub_rows, hw_pad;
 };
 
+// Folds `buffered` parked candidates into the running best 32.  Out of line and by value: the sorting network is
+// long, and merge_query has many call sites for it (instruction-cache footprint of the readout kernel).
+static __device__ __noinline__ WarpTop32 drain_buffer(WarpTop32 top, const float *buf_s, const int *buf_i, int buffered, int lane) {
+  __syncwarp();
+  for (int off = 0; off < buffered; off += 32) {
+    const bool ok = off + lane < buffered;
+    top.push(ok ? buf_s[off + lane] : -INFINITY, ok ? buf_i[off + lane] : 0x7fffffff, lane);
+  }
+  __syncwarp();
+  return top;
+}
+
 // One warp folds the lists of query q into the exact best 32 (best first, one per lane).
 // All loads (<= MERGE_MAX_SPLITS x 64 slots per batch) are issued up front; candidates below the shared threshold
 // (min over splits of the published r-th best: a lower bound of the true 32nd best, see select_tc.cu) are dropped
@@ -26,13 +38,8 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
   top.init();
   int buffered = 0;
   auto drain = [&]() {
-    __syncwarp();
-    for (int off = 0; off < buffered; off += 32) {
-      const bool ok = off + lane < buffered;
-      top.push(ok ? buf_s[off + lane] : -INFINITY, ok ? buf_i[off + lane] : 0x7fffffff, lane);
-    }
+    top = drain_buffer(top, buf_s, buf_i, buffered, lane);
     buffered = 0;
-    __syncwarp();
   };
   float tau = INFINITY;
   bool tau_ready = false;

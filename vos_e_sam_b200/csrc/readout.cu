@@ -87,7 +87,7 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
   int64_t gi = -1;
   if (q < a.hw) {
     if (FUSED) {
-      const WarpTop32 top = merge_query<16>(a.lists, q, m_s, m_i, lane);
+      const WarpTop32 top = merge_query<8>(a.lists, q, m_s, m_i, lane);
       if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
     } else if (lane < a.top_k) {
       s = a.score[(int64_t)q * a.top_k + lane];
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
   __shared__ float s_w[RQ][32];
   __shared__ const T *s_row[RQ][32];
   __shared__ int s_any[RQ];
-  __shared__ float s_out[RCH][RQ + 1];
+  __shared__ __align__(16) float s_out[RQ][RCH + 8];   // query-major, pitch chosen so that both the vector stores of the
+                                                      // gather and the transposed reads of the write-out are conflict-free
   __shared__ float m_s[FUSED ? RQ : 1][FUSED ? MERGE_BUF : 1];
   __shared__ int m_i[FUSED ? RQ : 1][FUSED ? MERGE_BUF : 1];
 
@@ -172,8 +173,14 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
             }
           }
         }
+        if (VEC % 4 == 0) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) s_out[c_local + v][qq] = acc[v];
+          for (int v = 0; v < VEC; v += 4)
+            *reinterpret_cast<float4 *>(&s_out[qq][c_local + v]) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s_out[qq][c_local + v] = acc[v];
+        }
       }
     }
     __syncthreads();
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArg
     for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
       const int c_local = e / RQ, qq = e % RQ;
       const int ch = ch0 + c_local, q = q0 + qq;
-      if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[c_local][qq];
+      if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[qq][c_local];
     }
     __syncthreads();
   }
