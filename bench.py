@@ -8,7 +8,8 @@ One JSON line on stdout (rank 0).  A "step" is one query frame: one match_memory
   value   query-frames/s with memory AND query resident in HBM; per-step CUDA-event times on the launch stream,
           L2 flushed (512 MiB write) before every timed step; max over ranks; whole-job aggregate over N GPUs.
   e2e     the same through the public API (MemoryManager.match_memory) with HOST buffers: pinned H2D of the
-          query key / selection and D2H of the readout inside the timed region, one sync per frame.
+          query key / selection and D2H of the readout of EVERY frame inside the timed region; two frames in
+          flight (the D2H copy of frame i overlaps the kernels of frame i + 1), wall clock over K frames.
   roofline      the dominant kernel (softmax_readout_kernel, HBM-bound) from its own per-launch event times
   roofline_similarity   the fused tcgen05 similarity + selection stage against the measured bf16 peak
   cpu_baseline  the oracle port of the reference (torch CPU) on this box's host cores, bounded sample
@@ -298,25 +299,43 @@ def run_ours(args, rank, world, local_rank):
         else:
             stage_events = events
         # ---- end-to-end through the public API with host buffers -------------------------------
+        # Two frames in flight: the D2H copy of frame i (copy stream, its own pinned buffer) overlaps the H2D copy and
+        # the kernels of frame i + 1; the host waits for frame i - 2's copy before that buffer is reused.
         e2e_steps = K
-        if not sharded:
-            def e2e_step(i):
-                a, b = host_q[i % pool]
-                r = mgr.match_memory(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
-                host_out.copy_(r, non_blocking=True)
-                torch.cuda.synchronize()
-        else:
-            def e2e_step(i):
-                a, b = host_q[i % pool]
-                r = engine.match(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
-                host_out.view(rows, hw)[:r.shape[0], :r.shape[1]].copy_(r, non_blocking=True)
-                torch.cuda.synchronize()
+        copy_stream = torch.cuda.Stream()
+        host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+        landed = [None, None]
+
+        def e2e_step(i):
+            a, b = host_q[i % pool]
+            qk_d, qe_d = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+            r = engine.match(qk_d, qe_d) if sharded else mgr.match_memory(qk_d, qe_d)
+            ready = torch.cuda.Event()
+            ready.record()
+            slot = i % 2
+            if landed[slot] is not None:
+                landed[slot].synchronize()      # the host has frame i - 2's readout
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                dst = host_outs[slot].view(rows, hw)[:r.shape[0], :r.shape[1]] if sharded else host_outs[slot]
+                dst.copy_(r, non_blocking=True)
+                r.record_stream(copy_stream)
+                landed[slot] = torch.cuda.Event()
+                landed[slot].record()
+
+        def e2e_drain():
+            for e in landed:
+                if e is not None:
+                    e.synchronize()
+            torch.cuda.synchronize()
         for i in range(W):
             e2e_step(i)
+        e2e_drain()
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             e2e_step(i)
+        e2e_drain()
         barrier()
         e2e_s = time.perf_counter() - t0
     step_ms = [e[0].elapsed_time(e[4]) for e in events]
