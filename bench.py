@@ -49,6 +49,14 @@ def peaks():
     return dict(hbm=6650.0, tflops=1590.0, source='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))[workload].get(kernel)
+    except Exception:
+        return None
+
+
 def xmem_config(**over):
     cfg = dict(hidden_dim=64, top_k=TOP_K, enable_long_term=True, enable_long_term_count_usage=True,
                max_mid_term_frames=10 ** 6, min_mid_term_frames=5, num_prototypes=128,
@@ -75,22 +83,48 @@ def fill_memory(mgr, gen, h, w, frames, n_obj, device, n_long=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML every 5 ms when pynvml is importable,
+    else the nvidia-smi query of the B200_PROFILING.md recipe (one sample per call, ~100 ms each)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = 'nvml'
+        except Exception:
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8), getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20), getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)]
+        self.rows.append([str(sm), str(mx)] + ['Active' if r & b else 'Not Active' for b in bits])
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        self.rows.append([c.strip() for c in out.strip().split(',')])
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(',')])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.005 if self.nvml else 0.1)
 
     def __enter__(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -103,18 +137,17 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
-                for nm, val in zip(names, r[2:6]):
+                for nm, val in zip(self.NAMES, r[2:6]):
                     if val.lower().startswith('active'):
                         reasons.add(nm)
             except Exception:
                 continue
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), source=self.source)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -366,11 +399,13 @@ def run_ours(args, rank, world, local_rank):
         rd_bytes = rows * min(n_mem, hw * TOP_K) * val_bytes / world + rows * hw * 4 / world + hw * TOP_K * 12
         sel_flops /= world
     roof_rd = dict(kernel='softmax_readout_kernel (merge + softmax + usage + sparse readout)', bound='hbm', achieved=rd_bytes / rd_t / 1e9, peak=pk['hbm'], unit='GB/s',
-                   frac=rd_bytes / rd_t / 1e9 / pk['hbm'], traffic=None, us_per_launch=rd_t * 1e6,
+                   frac=rd_bytes / rd_t / 1e9 / pk['hbm'], traffic=ncu_traffic(args.workload, 'softmax_readout_kernel') if world == 1 else None,
+                   us_per_launch=rd_t * 1e6,
                    algorithmic_bytes=rd_bytes, peak_source=pk['source'])
     roof_sel = dict(kernel='select_tc_kernel', bound='tensor',
                     achieved=sel_flops / sel_t / 1e12, peak=pk['tflops'], unit='TFLOP/s',
-                    frac=sel_flops / sel_t / 1e12 / pk['tflops'], traffic=None, us_per_launch=sel_t * 1e6,
+                    frac=sel_flops / sel_t / 1e12 / pk['tflops'], traffic=ncu_traffic(args.workload, 'select_tc_kernel') if world == 1 else None,
+                    us_per_launch=sel_t * 1e6,
                     algorithmic_flops=sel_flops, executed_flop_multiplier=25.0 / 8.0, peak_source=pk['source'] + ', burst')
     dominant, other = (roof_rd, roof_sel) if rd_t >= sel_t else (roof_sel, roof_rd)
     cpu = None

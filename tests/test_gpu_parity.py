@@ -99,6 +99,30 @@ def test_select_topk_vs_oracle(vos, path, n, h, w, k):
     assert frac > 0.5
 
 
+@pytest.mark.parametrize('hw,splits', [(16000, 1), (8160, 2), (6000, 3), (4700, 4), (3700, 5), (2500, 7), (1620, 11),
+                                       (500, 23)])
+def test_select_tc_every_rank_variant_matches_simt(vos, hw, splits):
+    """The tcgen05 kernel is instantiated per published rank R = ceil(33 / (2 * splits)); the query count picks the
+    number of key splits (148 SMs / query tiles) and with it the variant.  Every variant must return the candidates
+    of the exact fp32 SIMT kernel (sets equal wherever the SIMT k / k+1 gap is decided), with scores within 2e-3."""
+    n = 6000
+    g = torch.Generator().manual_seed(4321 + hw)
+    mk, ms, _ = synth.keys(g, n)
+    qk = torch.randn(1, 64, hw, generator=g)
+    qe = torch.sigmoid(torch.randn(1, 64, hw, generator=g))
+    store = vos.KeyValueMemoryStore(count_usage=False)
+    store.add(dev(mk), [torch.zeros(1, 8, n, device='cuda')], dev(ms), None, None)
+    seg = [store.key_segment(0, n)]
+    q2, e2 = qk.cuda()[0], qe.cuda()[0]
+    s_tc, i_tc = vos.ops.select_topk(q2, e2, seg, 30, path=vos.N.PATH_TCGEN05)
+    s_si, i_si = vos.ops.select_topk(q2, e2, seg, 31, path=vos.N.PATH_SIMT)      # 31st score -> the k / k+1 gap
+    torch.testing.assert_close(s_tc, s_si[:, :30], rtol=0, atol=2e-3)
+    decided = (s_si[:, 29] - s_si[:, 30]) > 2 * GAP
+    same = (torch.sort(i_tc, 1).values == torch.sort(i_si[:, :30], 1).values).all(1)
+    assert float(decided.float().mean()) > 0.5
+    assert not bool((decided & ~same).any()), f'{int((decided & ~same).sum())} decided queries differ (splits={splits})'
+
+
 @pytest.mark.parametrize('path', ['simt', 'tcgen05'])
 def test_select_redundant_video(vos, path):
     """Near-duplicate memory frames (static background): many near-ties around the k-th score."""
