@@ -273,8 +273,7 @@ def run_ours(args, rank, world, local_rank):
             qk, qe = dev_q[i % pool]
             flush.fill_(i & 0xFF)
             ev[0].record()
-            engine.match(qk, qe, events=ev)
-            ev[3].record()
+            engine.match(qk, qe, events=ev[1:4])    # after local select / exchange + merge / readout
             ev[4].record()
         launches_per_step = engine.launches_per_match
 
@@ -373,9 +372,13 @@ def run_ours(args, rank, world, local_rank):
         e2e_s = time.perf_counter() - t0
     step_ms = [e[0].elapsed_time(e[4]) for e in events]
     se = stage_events
-    pack_ms = [e[0].elapsed_time(e[1]) for e in se]
+    # davis5: [begin, after pack, after select, after readout, end]; sharded: [begin, after pack + select, after
+    # exchange + merge, after readout, end]
+    pack_ms = [e[0].elapsed_time(e[1]) for e in se] if not sharded else [0.0 for e in se]
     sel_ms = [e[1].elapsed_time(e[2]) for e in se] if not sharded else [e[0].elapsed_time(e[1]) for e in se]
-    rd_ms = [e[2].elapsed_time(e[3]) for e in se] if not sharded else [e[1].elapsed_time(e[2]) for e in se]
+    rd_ms = [e[2].elapsed_time(e[3]) for e in se]
+    xchg_ms = [e[1].elapsed_time(e[2]) for e in se] if sharded else None
+
     total_ms = sum(step_ms)
 
     stats = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
@@ -396,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
     sel_flops = 4.0 * n_mem * hw * CK
     sel_t = statistics.mean(sel_ms) / 1000.0
     if sharded:
-        rd_bytes = rows * min(n_mem, hw * TOP_K) * val_bytes / world + rows * hw * 4 / world + hw * TOP_K * 12
+        rd_bytes = rows * min(n_mem, hw * TOP_K) * val_bytes + rows * hw * 4 + hw * TOP_K * 12   # readout is replicated
         sel_flops /= world
     roof_rd = dict(kernel='softmax_readout_kernel (merge + softmax + usage + sparse readout)', bound='hbm', achieved=rd_bytes / rd_t / 1e9, peak=pk['hbm'], unit='GB/s',
                    frac=rd_bytes / rd_t / 1e9 / pk['hbm'], traffic=ncu_traffic(args.workload, 'softmax_readout_kernel') if world == 1 else None,
@@ -406,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
                     achieved=sel_flops / sel_t / 1e12, peak=pk['tflops'], unit='TFLOP/s',
                     frac=sel_flops / sel_t / 1e12 / pk['tflops'], traffic=ncu_traffic(args.workload, 'select_tc_kernel') if world == 1 else None,
                     us_per_launch=sel_t * 1e6,
-                    algorithmic_flops=sel_flops, executed_flop_multiplier=25.0 / 8.0, peak_source=pk['source'] + ', burst')
+                    algorithmic_flops=sel_flops, executed_flop_multiplier=25.0 / 8.0, executed_frac=25.0 / 8.0 * sel_flops / sel_t / 1e12 / pk['tflops'], peak_source=pk['source'] + ', burst')
     dominant, other = (roof_rd, roof_sel) if rd_t >= sel_t else (roof_sel, roof_rd)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -422,6 +425,8 @@ def run_ours(args, rank, world, local_rank):
                 roofline_other=other, cpu_baseline=cpu,
                 stage_us=dict(pack_query=statistics.mean(pack_ms) * 1e3, select=statistics.mean(sel_ms) * 1e3,
                               readout=statistics.mean(rd_ms) * 1e3,
+                              **(dict(exchange_and_merge=statistics.mean(xchg_ms) * 1e3,
+                                      note='select includes the query packing kernel') if sharded else {}),
                               step_median=statistics.median(step_ms) * 1e3,
                               step_kernel_by_kernel=statistics.median(e[0].elapsed_time(e[4]) for e in se) * 1e3))
     print(json.dumps(line), flush=True)

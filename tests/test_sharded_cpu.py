@@ -93,4 +93,3 @@ def test_partition_helpers():
     assert covered == list(range(1000))
     assert sh.shard_bounds(64, 4, 2) == (64, 64)                              # empty shard
     assert sorted(sum((sh.partition_sequences(64, 8, r) for r in range(8)), [])) == list(range(64))
-    assert [sh.query_slice(8160, 8, r) for r in (0, 7)] == [(0, 1024), (7168, 8160)]

@@ -7,11 +7,11 @@ Two ways the path shards:
 
 2. one LVOS-scale long-term bank sharded along N (``ShardedLongTermReadout``):
      rank r owns keys [lo_r, hi_r) (packed image + fp32 keys) -> fused similarity + LOCAL top-k
-     all-gather of the (score, global index) candidates: HW * k * 12 bytes per rank
+     all-gather of the (score, global index) candidates: HW * k * 8 bytes per rank
      every rank merges the G candidate lists -> the same global top-k (vosmem_merge_topk)
-     softmax + readout of a slice of the query rows per rank from a replicated value shadow,
-     then an all-gather of the output slices (no reduction anywhere: global top-k is a subset of the
-     union of local top-k's, and the softmax needs only the k merged scores).
+     softmax + readout on every rank from a replicated value shadow (no second collective and no reduction
+     anywhere: global top-k is a subset of the union of local top-k's, and the softmax needs only the k
+     merged scores).
    The reference has no counterpart (single GPU, tools/runner.py:32); results equal the unsharded
    MemoryManager.match_memory by construction, which the tests check.
 
@@ -37,13 +37,6 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 64) -> Tuple[int, i
 def partition_sequences(n_sequences: int, world: int, rank: int) -> List[int]:
     """Round-robin deal of independent sequences to ranks (data parallel, no collective)."""
     return list(range(rank, n_sequences, world))
-
-
-def query_slice(hw: int, world: int, rank: int, align: int = 16) -> Tuple[int, int]:
-    per = -(-hw // world)
-    per = -(-per // align) * align
-    lo = min(hw, rank * per)
-    return lo, min(hw, lo + per)
 
 
 class CudaBackend:
@@ -114,7 +107,8 @@ class ShardedLongTermReadout:
         return out.view((self.world,) + tuple(t.shape))
 
     def match(self, query_key, selection, events=None) -> torch.Tensor:
-        """query_key / selection: 1 x CK x h x w  ->  rows x HW (full readout on every rank)."""
+        """query_key / selection: 1 x CK x h x w  ->  rows x HW (full readout on every rank).
+        events (optional, for bench.py): [after local select, after exchange + merge, after readout]."""
         h, w = query_key.shape[-2:]
         hw = h * w
         qk = query_key.flatten(start_dim=2)[0]
@@ -125,20 +119,25 @@ class ShardedLongTermReadout:
         else:  # empty shard: contributes no candidates
             score = torch.full((hw, k), float('-inf'), dtype=torch.float32, device=qk.device)
             index = torch.full((hw, k), -1, dtype=torch.int64, device=qk.device)
-        # ---- the one exchange step: all-gather of the local top-k candidates ----
-        all_s, all_i = self._all_gather(score), self._all_gather(index)
+        if events is not None:
+            events[0].record()
+        # ---- the one exchange step: all-gather of the local top-k candidates (one message: fp32 score bits and
+        #      the global index as int32 pairs, HW * k * 8 bytes per rank) ----
+        if self.world == 1:
+            all_s, all_i = score.unsqueeze(0), index.unsqueeze(0)
+        else:
+            packed = torch.stack((score.view(torch.int32), index.to(torch.int32)))     # 2 x HW x k
+            gathered = self._all_gather(packed)                                          # world x 2 x HW x k
+            all_s = gathered[:, 0].contiguous().view(torch.float32)
+            all_i = gathered[:, 1].to(torch.int64)
         g_score, g_index = self.backend.merge(all_s, all_i)            # identical on every rank
         if events is not None:
             events[1].record()
-        # ---- readout of this rank's slice of the query rows, then all-gather of the slices ----
-        qlo, qhi = query_slice(hw, self.world, self.rank)
-        per = query_slice(hw, self.world, 0)[1]
-        part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
-        if qhi > qlo:
-            self.backend.readout(g_score[qlo:qhi], g_index[qlo:qhi], self.rows, self.n_total, out=part[:, :qhi - qlo])
+        # ---- readout: values are replicated, so every rank reads out all query rows itself.  (Slicing the query
+        #      rows over the ranks and all-gathering rows x HW fp32 afterwards was measured slower at 2 GPUs: 24 us
+        #      for the half readout + 56 us for the 16.7 MB gather against 35 us for the whole readout.) ----
+        out = torch.empty((self.rows, hw), dtype=torch.float32, device=qk.device)
+        self.backend.readout(g_score, g_index, self.rows, self.n_total, out=out)
         if events is not None:
             events[2].record()
-        if self.world == 1:
-            return part[:, :hw]
-        gathered = self._all_gather(part)                               # world x rows x per
-        return gathered.permute(1, 0, 2).reshape(self.rows, self.world * per)[:, :hw]
+        return out
