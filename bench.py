@@ -264,10 +264,10 @@ def run_ours(args, rank, world, local_rank):
             flush.fill_(i & 0xFF)
             # the C call records ev[0..3] on the stream around its pack / select / readout kernels
             N.lib.vosmem_debug_set_stage_events(ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event, ev[3].cuda_event)
-            ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # pack_query, tcgen05 select, merge+softmax+readout
+            ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout
             work.age()                                          # life_count += 1
             ev[4].record()
-        launches_per_step = 4
+        launches_per_step = 3                                   # select_tc (packs its query tile), softmax_readout, age
     else:
         def step(i, ev):
             qk, qe = dev_q[i % pool]

@@ -23,10 +23,21 @@ torch.cuda.synchronize()
 N.lib.vosmem_debug_set_timing_buffer(None)
 d = dbg.view(-1, 32).cpu()
 d = d[(d != 0).any(1)]
-names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls']
+names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls', 'prologue', 'cta_total', 'g_start', 'g_end', 't_first_publish(q1h0)', 't_refresher_all_valid', 'refresher_iter_all_valid', 't_refresher_iter0_done']
 print('CTAs', d.shape[0])
 st = d[:, 15]
 print('warp1 first-tile wait cycles: mean', float(st.float().mean()), 'max', int(st.max()))
 for i, nm in enumerate(names):
     col = d[:, i].float()
     print(f'{nm:16s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f}')
+
+start, end = d[:, 23].double(), d[:, 24].double()
+t0 = float(start.min())
+print(f'global timer (us): first CTA start 0, last CTA start {float(start.max()) - t0:.0f} ns, first CTA end {float(end.min()) - t0:.0f} ns, '
+      f'last CTA end {float(end.max()) - t0:.0f} ns')
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ts = []
+for _ in range(5):
+    ev0.record(); ops.select_topk(q2, e2, seg, 30, path=N.PATH_TCGEN05); ev1.record(); torch.cuda.synchronize()
+    ts.append(ev0.elapsed_time(ev1) * 1e3)
+print('select_topk (pack + select + merge) event time us:', ts)

@@ -1,4 +1,6 @@
 // extern "C" entry points that tie the kernels into the calls declared in include/vosmem.h.
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -110,9 +112,13 @@ static int run_selection(const vosmem_select_desc *d, cudaStream_t st, Workspace
   const int splits = choose_splits(path, d->hw, total);
   n_lists = splits;                                                          // candidate lists left per query
   n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : splits;   // published threshold rows
+  static std::atomic<uint32_t> epoch_counter{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count() | 1u};
+  ws.epoch = epoch_counter.fetch_add(1, std::memory_order_relaxed);   // tags this launch's published thresholds (PubEntry)
   if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
-  rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
-  if (rc != VOSMEM_OK) return rc;
+  if (path != VOSMEM_PATH_TCGEN05) {   // the tcgen05 kernel packs its query tile itself
+    rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
+    if (rc != VOSMEM_OK) return rc;
+  }
   if (g_stage_events[1]) cudaEventRecord(g_stage_events[1], st);
   rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(*d, ws, splits, st) : launch_select_simt(*d, ws, splits, st);
   if (rc != VOSMEM_OK) return rc;

@@ -139,9 +139,27 @@ struct CandEntry {   // one exchanged candidate: score + index on the candidate 
 };
 static_assert(sizeof(CandEntry) == 8, "exchange entries are read / written as 8-byte words");
 
+// A published threshold (select_tc.cu, "Thresholds") is only meaningful for the launch that wrote it: the entry
+// carries that launch's epoch and reads of any other epoch see -inf.  The workspace therefore needs no reset
+// between calls (and no initialisation: a stale or uninitialised entry matches the 32-bit epoch of the current
+// launch only by a 2^-32 accident).
+struct PubEntry {
+  float value;
+  uint32_t epoch;
+};
+static_assert(sizeof(PubEntry) == 8, "published thresholds are read / written as 8-byte words");
+__device__ __forceinline__ float pub_load(const PubEntry *p, uint32_t epoch) {
+  const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(p));
+  return v.y == epoch ? __uint_as_float(v.x) : -INFINITY;
+}
+__device__ __forceinline__ void pub_store(PubEntry *p, float value, uint32_t epoch) {
+  __stcg(reinterpret_cast<uint2 *>(p), make_uint2(__float_as_uint(value), epoch));
+}
+
 struct Workspace {
   unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
-  float *pub;                  // splits_cap * hw_pad: r-th best score published per (split, query), -inf = none yet
+  PubEntry *pub;               // pub_rows * hw_pad: lower bound published per (virtual split, query) by the current launch
+  uint32_t epoch;              // of the current launch (set by run_selection)
   CandEntry *cand;             // splits * hw_pad * CAND_SLOTS
   int *cand_count;             // splits * hw_pad
   int pub_rows;                // rows of `pub` (= splits_cap * LISTS_PER_SPLIT)
@@ -172,7 +190,8 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
     return r;
   };
   w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
-  w.pub = reinterpret_cast<float *>(take(cap * hw_pad * 4));
+  w.pub = reinterpret_cast<PubEntry *>(take(cap * hw_pad * 8));
+  w.epoch = 0;
   w.pub_rows = (int)cap;
   w.cand = reinterpret_cast<CandEntry *>(take((int64_t)splits_cap(hw) * hw_pad * CAND_SLOTS * 8));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));

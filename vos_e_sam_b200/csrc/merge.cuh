@@ -10,8 +10,9 @@ constexpr int MERGE_BUF = 128;
 struct SplitLists {
   const CandEntry *cand;    // [splits][hw_pad][CAND_SLOTS]
   const int *cand_count;    // [splits][hw_pad]
-  const float *pub;         // [pub_rows][hw_pad] published lower bounds per (virtual split, query); -inf = none
+  const PubEntry *pub;      // [pub_rows][hw_pad] published lower bounds per (virtual split, query) of launch `epoch`
   int splits, pub_rows, hw_pad;
+  uint32_t epoch;
 };
 
 // Folds `buffered` parked candidates into the running best 32.  Out of line and by value: the sorting network is
@@ -57,7 +58,7 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
       }
     }
     if (!tau_ready) {  // lane y owns list y
-      for (int y = lane; y < L.pub_rows; y += 32) tau = fminf(tau, L.pub[(int64_t)y * L.hw_pad + q]);
+      for (int y = lane; y < L.pub_rows; y += 32) tau = fminf(tau, pub_load(L.pub + (int64_t)y * L.hw_pad + q, L.epoch));
       tau = warp_min(tau);
       tau_ready = true;
     }

@@ -60,17 +60,15 @@ __global__ void pack_keys_kernel(const float *__restrict__ key, int64_t key_ld, 
 }
 
 // Block = 32 queries x 8 channel groups (coalesced 128-byte reads of qk / qe).  Produces the fp32 vector for the
-// SIMT path (c-major: qvec[c * hw_pad + q]), the bf16 image for the tcgen05 path and resets the published
-// thresholds.  Image chunk order: [y1_hi | y2_hi | y1_lo | y2_lo | tail | 0] with y1 = -e, y2 = 2 q e,
+// SIMT path (c-major: qvec[c * hw_pad + q]) and the bf16 image (the tcgen05 kernel packs its own query tile in its
+// prologue; the image is kept for the tile self-test).  Image chunk order: [y1_hi | y2_hi | y1_lo | y2_lo | tail | 0] with y1 = -e, y2 = 2 q e,
 // tail = (y3_hi, y3_lo, y3_hi, 0...), y3 = -sum e q^2.
 __global__ void __launch_bounds__(256) pack_query_kernel(const float *__restrict__ qk, const float *__restrict__ qe,
-                                                         int ck, int hw, int hw_pad, int pub_rows,
-                                                         float *__restrict__ qvec, unsigned char *__restrict__ image,
-                                                         float *__restrict__ pub) {
+                                                         int ck, int hw, int hw_pad,
+                                                         float *__restrict__ qvec, unsigned char *__restrict__ image) {
   __shared__ float red[8][33];
   const int ql = threadIdx.x, gy = threadIdx.y;
   const int q = blockIdx.x * 32 + ql;
-  for (int y = gy; y < pub_rows; y += 8) pub[(int64_t)y * hw_pad + q] = -INFINITY;
   const bool live = q < hw;
   const bool img = (ck == CK_TC);
   unsigned char *tile = image + (int64_t)(q / TQ) * QUERY_TILE_BYTES;
@@ -159,7 +157,7 @@ __global__ void age_kernel(float *__restrict__ life, int64_t n) {
 
 int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st) {
   int hw_pad = (int)round_up64(hw, TQ);
-  pack_query_kernel<<<hw_pad / 32, dim3(32, 8), 0, st>>>(qk, qe, ck, hw, hw_pad, ws.pub_rows, ws.qvec, ws.query_image, ws.pub);
+  pack_query_kernel<<<hw_pad / 32, dim3(32, 8), 0, st>>>(qk, qe, ck, hw, hw_pad, ws.qvec, ws.query_image);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
@@ -219,8 +217,6 @@ extern "C" int vosmem_debug_pack_query(const float *query_key, const float *quer
   int64_t n_qtiles = ceil_div64(hw, TQ), hw_pad = n_qtiles * TQ;
   unsigned char *p = static_cast<unsigned char *>(image);
   ws.query_image = p;
-  ws.pub = reinterpret_cast<float *>(p + n_qtiles * QUERY_TILE_BYTES);
-  ws.pub_rows = 1;
   ws.qvec = reinterpret_cast<float *>(p + n_qtiles * QUERY_TILE_BYTES + hw_pad * 4);
   return launch_pack_query(query_key, query_selection, ck, hw, ws, (cudaStream_t)stream);
 }

@@ -247,7 +247,7 @@ int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int 
   bool vec_ok;
   int rc = fill_args(d, a, vec_ok);
   if (rc != VOSMEM_OK) return rc;
-  a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(d->hw, TQ)};
+  a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(d->hw, TQ), ws.epoch};
   return launch<4, true>(a, d->value_dtype, vec_ok, st);
 }
 

@@ -4,8 +4,10 @@
 // object group: the N x HW similarity matrix only ever exists as 128 x 64 fp32 tiles in tensor memory.
 //
 //   grid  = (query tiles of 128, N-splits)        one CTA per SM (~200 KB shared memory), 11 warps
-//   warp 8  producer : cp.async.bulk (TMA) of the query image (once) and the streamed key tiles,
-//                      mbarrier full/empty ring of STAGES stages
+//   prologue         : warps 0-7 pack the CTA's 128-query tile ([-e | 2 q e | -sum e q^2] as bf16 hi / lo, the
+//                      shared-memory layout of a K-major no-swizzle UMMA operand) straight from the fp32 query key /
+//                      selection -- no separate packing kernel, no query image in global memory
+//   warp 8  producer : cp.async.bulk (TMA) of the streamed key tiles, mbarrier full/empty ring of STAGES stages
 //   warp 9  MMA      : copies the query operand into tensor memory once (tcgen05.cp), then per key tile
 //                      25 tcgen05.mma (M128 N64 K16, A from TMEM, B from shared memory; bf16 hi/lo split
 //                      -> fp32) into one of ACC_BUFS accumulator buffers, tcgen05.commit -> mbarriers
@@ -52,6 +54,7 @@ constexpr int SORT_ABOVE = CSLOTS - 16;     // lists still longer than this afte
 constexpr uint32_t SS = CS_E * 8;      // byte stride between consecutive slots of one list
 constexpr uint32_t KEY_SLOT_MASK = 63u;           // low bits of a sort key hold the slot id
 constexpr int FIRST_WAIT_CYCLES = 20000;
+constexpr int RB = 11;                            // published rows the refresher warp reads per batch (DAVIS: 22 rows = 2 batches)
 constexpr int TRACK_TILES = 16;                   // tiles per warp set during which the subsets' best scores are tracked          // bounded wait for the other splits' first publication
 
 // shared memory map (bytes)
@@ -85,8 +88,9 @@ struct TcArgs {
   int64_t len0;
   int64_t tiles_total;
   int hw, hw_pad, splits;
-  const unsigned char *query_image;
-  float *pub;          // [splits][hw_pad] published lower bound per (split, query): see "Thresholds"
+  const float *qk, *qe;   // query key / selection, CK x hw fp32 (qe may be NULL: isotropic)
+  PubEntry *pub;          // [virtual splits][hw_pad] published lower bound per (virtual split, query): see "Thresholds"
+  uint32_t epoch;         // tags this launch's published values
   CandEntry *cand;
   int *cand_count;
   long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
@@ -252,6 +256,71 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
   return st;
 }
 
+// Warps 0-7 (256 threads): the query operand of this CTA's 128 queries, written in place as the shared-memory image
+// the tcgen05.cp copies expect.  Row y[q] = [-e | 2 q e | -sum_c e q^2] (memory_util.py:20-27; e = 1 and no last term
+// when there is no selection, :28-32), every fp32 entry as a bf16 (hi, lo) pair; 16-byte chunk order per row:
+// [y1_hi 0-7 | y2_hi 8-15 | y1_lo 16-23 | y2_lo 24-31 | tail 32 | 0 33], tail = (y3_hi, y3_lo, y3_hi, 0...).
+// Thread = (query row, half of the channels); loads are coalesced over the rows, stores are conflict-free.
+__device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsigned char *tile, float *red) {
+  const int r = threadIdx.x & (TQ - 1), hsel = threadIdx.x >> 7;
+  const int q = qtile * TQ + r;
+  const bool live = q < a.hw;
+  // all 64 loads are issued before the first use (no branch in between): rows past the end read the last query
+  // and are zeroed afterwards
+  float kk[32], ee[32];
+  const int64_t col = live ? q : a.hw - 1;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) kk[j] = __ldg(a.qk + (int64_t)(hsel * 32 + j) * a.hw + col);
+  if (a.qe) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ee[j] = __ldg(a.qe + (int64_t)(hsel * 32 + j) * a.hw + col);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ee[j] = 1.f;
+  }
+  if (!live) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) kk[j] = ee[j] = 0.f;
+  }
+  float y3 = 0.f;
+#pragma unroll
+  for (int gg = 0; gg < 4; ++gg) {
+    const int g = hsel * 4 + gg;
+    uint32_t h1[4], l1[4], h2[4], l2[4];
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      __nv_bfloat16 hi[2][2], lo[2][2];   // [y1 | y2][element of the pair]
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float k = kk[gg * 8 + jp * 2 + u], e = ee[gg * 8 + jp * 2 + u];
+        split_bf16(-e, hi[0][u], lo[0][u]);
+        split_bf16(2.0f * (k * e), hi[1][u], lo[1][u]);
+        if (a.qe) y3 -= e * (k * k);
+      }
+      auto pack2 = [](__nv_bfloat16 x, __nv_bfloat16 y) {
+        return (uint32_t)__bfloat16_as_ushort(x) | ((uint32_t)__bfloat16_as_ushort(y) << 16);
+      };
+      h1[jp] = pack2(hi[0][0], hi[0][1]); l1[jp] = pack2(lo[0][0], lo[0][1]);
+      h2[jp] = pack2(hi[1][0], hi[1][1]); l2[jp] = pack2(lo[1][0], lo[1][1]);
+    }
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, g)) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 8 + g)) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 16 + g)) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 24 + g)) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+  }
+  if (hsel == 1) red[r] = y3;
+  asm volatile("bar.sync 6, 256;" ::: "memory");   // the eight packing warps
+  if (hsel == 0) {
+    y3 += red[r];
+    __nv_bfloat16 hi, lo;
+    split_bf16(y3, hi, lo);
+    const uint32_t h = __bfloat16_as_ushort(hi), l = __bfloat16_as_ushort(lo);
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 32)) = make_uint4(h | (l << 16), h, 0u, 0u);
+    *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 33)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  ptx::fence_proxy_async();   // the tcgen05.cp copies read the image through the async proxy
+}
+
 template <int R>   // R = tracked / published rank per virtual split (see "Thresholds")
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -272,6 +341,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
   const int n_tiles = (int)(g_hi - g_lo);
   long long *dbg = a.dbg ? a.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  const long long t_entry = clock64();
+  unsigned long long g_entry = 0;
+  if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_empty + i, 1); }
@@ -287,45 +359,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (warp < EPI_WARPS) pack_query_tile(a, qtile, smem + SM_Q, reinterpret_cast<float *>(smem + SM_NA));
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(FULL, *tmem_slot, 0);   // provably warp-uniform
+  if (dbg && threadIdx.x == 0) dbg[21] = clock64() - t_entry;   // prologue
 
   if (warp == W_REFRESH) {
     // ===== threshold refresher: tau_sh[row] = min over the virtual splits of their published lower bound =====
     // (a stale value is still a valid lower bound, so no ordering with the epilogue is needed)
-    const float *pub_row = a.pub + qtile * TQ + lane;
+    const PubEntry *pub_row = a.pub + qtile * TQ + lane;
     for (int it = 0; *epi_done < EPI_WARPS; ++it) {
       float m[TQ / 32];
 #pragma unroll
       for (int h = 0; h < TQ / 32; ++h) m[h] = INFINITY;
-      for (int y0 = 0; y0 < vsplits; y0 += 8) {
+      for (int y0 = 0; y0 < vsplits; y0 += RB) {
+        // RB x 4 independent 8-byte loads in flight per lane: rows past the end re-read the last row (harmless for a
+        // minimum), so there is no branch between the loads and they are all issued before the first use
+        uint2 raw[RB][TQ / 32];
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {   // 32 independent loads in flight per lane
-          if (y0 + y < vsplits) {
+        for (int y = 0; y < RB; ++y) {
+          const int yy = min(y0 + y, vsplits - 1);
 #pragma unroll
-            for (int h = 0; h < TQ / 32; ++h)
-              m[h] = fminf(m[h], __ldcg(pub_row + (int64_t)(y0 + y) * a.hw_pad + 32 * h));
-          }
+          for (int h = 0; h < TQ / 32; ++h)
+            raw[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub_row + (int64_t)yy * a.hw_pad + 32 * h));
         }
+#pragma unroll
+        for (int y = 0; y < RB; ++y)
+#pragma unroll
+          for (int h = 0; h < TQ / 32; ++h)
+            m[h] = fminf(m[h], raw[y][h].y == a.epoch ? __uint_as_float(raw[y][h].x) : -INFINITY);
       }
 #pragma unroll
       for (int h = 0; h < TQ / 32; ++h) tau_sh[lane + 32 * h] = m[h];
+      if (dbg) {
+        bool all_ok = true;
+#pragma unroll
+        for (int h = 0; h < TQ / 32; ++h) all_ok = all_ok && m[h] != -INFINITY;
+        if (__all_sync(FULL, all_ok) && dbg[26] == 0 && lane == 0) { dbg[26] = clock64() - t_entry; dbg[27] = it; }
+        if (it == 0 && lane == 0) dbg[28] = clock64() - t_entry;
+      }
       if (it >= 16) __nanosleep(256);   // thresholds move fastest during the first tiles
     }
   } else if (warp == W_PRODUCER) {
     // ===== producer =====
     if (lane == 0 && n_tiles > 0) {
-      // the query image first, staged in key stages 0-1 until the MMA thread has copied it to tensor memory
-      ptx::mbar_arrive_expect_tx(bar_q, QUERY_TILE_BYTES);
-      const unsigned char *qsrc = a.query_image + (int64_t)qtile * QUERY_TILE_BYTES;
-      ptx::bulk_g2s(smem + SM_Q, qsrc, QUERY_TILE_BYTES / 2, bar_q);
-      ptx::bulk_g2s(smem + SM_Q + QUERY_TILE_BYTES / 2, qsrc + QUERY_TILE_BYTES / 2, QUERY_TILE_BYTES / 2, bar_q);
-      ptx::mbar_wait_backoff(bar_qdone, 0, 64);
+      // stages 0-1 hold the query image until the MMA warp has copied it to tensor memory: key tile i goes to stage
+      // (i + 2) % STAGES, so the first key tile streams in meanwhile
       long long t_wait = 0;
       for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % STAGES;
+        const int st = (i + 2) % STAGES;
+        if (i == 1) ptx::mbar_wait_backoff(bar_qdone, 0, 64);
         const long long t0 = clock64();
         ptx::mbar_wait_backoff(bar_empty + st, ((i / STAGES) & 1) ^ 1, 128);
         t_wait += clock64() - t0;
@@ -343,14 +428,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     //       the uniform-register operands of UTCHMMA need no per-instruction waterfall loop); one elected lane issues
     if (n_tiles > 0) {
       const uint32_t tmem_a = tmem_base + TMEM_A;
-      ptx::mbar_wait(bar_q, 0);
-      ptx::tc_fence_after();
-      stage_query_in_tmem(ptx::smem_u32(smem + SM_Q), tmem_a);
+      stage_query_in_tmem(ptx::smem_u32(smem + SM_Q), tmem_a);   // the image was packed before the CTA-wide barrier
       ptx::umma_commit_elect(bar_qdone);   // arrives once the copies have read shared memory
       long long t_acc = 0, t_ld = 0, t_issue = 0;
       const long long t_begin = clock64();
       for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % STAGES, buf = i % ACC_BUFS;
+        const int st = (i + 2) % STAGES, buf = i % ACC_BUFS;
         const long long t0 = clock64();
         ptx::mbar_wait_backoff(bar_tempty + buf, ((i / ACC_BUFS) & 1) ^ 1, 64);
         const long long t1 = clock64();
@@ -381,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
     float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
 #pragma unroll
     for (int u = 0; u < R; ++u) best[u] = -INFINITY;
-    float *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
+    PubEntry *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
     long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
     int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
@@ -463,8 +546,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
       }
       if (best[R - 1] > st.pub) {
         st.pub = best[R - 1];
-        pub_mine[lane] = st.pub;
+        pub_store(pub_mine + lane, st.pub, a.epoch);
       }
+      if (dbg && n_done == 0 && lane == 0 && quarter == 1 && half == 0) dbg[25] = clock64() - t_entry;
       if (R <= 3 && n_done == 0) {
         // First tile of this set with many splits: nothing is known yet and every score would be kept.  The tile
         // sits in registers, so give the other splits a bounded moment to publish their first values (the MMA warp
@@ -514,7 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
               const long long tr0 = clock64();
               const float pub_before = st.pub;
               st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
-              if (st.pub > pub_before) pub_mine[lane] = st.pub;
+              if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, a.epoch);
               t_relieve += clock64() - tr0;
               ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
@@ -578,6 +662,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long g_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+    dbg[22] = clock64() - t_entry;   // whole CTA
+    dbg[23] = (long long)g_entry;    // ns, global timer: CTA start / end (spread of the starts, tail of the grid)
+    dbg[24] = (long long)g_exit;
+  }
 }
 
 // Self-test: raw accumulator tile of query tile 0 against key tile 0 through the same staging + MMA sequence.
@@ -659,8 +750,10 @@ int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int split
   a.hw = d.hw;
   a.hw_pad = (int)round_up64(d.hw, TQ);
   a.splits = splits;
-  a.query_image = ws.query_image;
+  a.qk = d.query_key;
+  a.qe = d.query_selection;
   a.pub = ws.pub;
+  a.epoch = ws.epoch;
   a.cand = ws.cand;
   a.cand_count = ws.cand_count;
   a.dbg = g_tc_debug;
