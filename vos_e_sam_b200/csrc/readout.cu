@@ -87,7 +87,7 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
   int64_t gi = -1;
   if (q < a.hw) {
     if (FUSED) {
-      const WarpTop32 top = merge_query<8>(a.lists, q, m_s, m_i, lane);
+      const WarpTop32 top = merge_query<12>(a.lists, q, m_s, m_i, lane);
       if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
     } else if (lane < a.top_k) {
       s = a.score[(int64_t)q * a.top_k + lane];
@@ -128,7 +128,7 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
 
 // grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
 template <typename T, int VEC, int RQ, bool FUSED>
-__global__ void __launch_bounds__(RTHREADS, 4) softmax_readout_kernel(ReadoutArgs a) {
+__global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(ReadoutArgs a) {
   constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering one pass of channels
   constexpr int GROUPS = RTHREADS / TPQ;                             // query groups working concurrently
   constexpr int CH_PER_PASS = TPQ * VEC;                             // <= RCH
