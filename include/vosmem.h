@@ -108,7 +108,8 @@ typedef struct vosmem_select_desc {
   vosmem_segment seg[VOSMEM_MAX_SEGMENTS];
   int64_t index_base;
   int path;                     /* enum vosmem_path                                            */
-  void *workspace;
+  void *workspace;        /* device scratch of >= vosmem_workspace_bytes(): contents need not be initialised nor
+                           * preserved between calls (published thresholds carry a per-launch epoch)        */
   int64_t workspace_bytes;
 } vosmem_select_desc;
 
