@@ -36,6 +36,7 @@ import torch  # noqa: E402
 
 CK, CV, TOP_K = 64, 512, 30
 DAVIS = dict(h=30, w=54, frames=10, n_obj=5)                       # BASELINE.json configs[1]
+BATCH = int(os.environ.get('VOSMEM_BENCH_BATCH', 11))                                                         # sequences per GPU of --workload davis_batch (configs[4]): 11 x 13 query tiles = 143 CTAs
 LVOS = dict(h=68, w=120, n_long=100_000, work_frames=0, n_obj=1)   # BASELINE.json configs[3]
 METRIC = 'memory_readout_query_frames_per_sec'
 UNIT = 'query-frames/s'
@@ -159,7 +160,7 @@ def cpu_reference_rate(workload, seconds_budget=12.0, min_calls=3, max_calls=40)
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(1234 + 2)
     ref = orc.Readout(xmem_config())
-    if workload == 'davis5':
+    if workload in ('davis5', 'davis_batch'):
         fill_memory(ref, g, DAVIS['h'], DAVIS['w'], DAVIS['frames'], DAVIS['n_obj'], 'cpu')
         h, w = DAVIS['h'], DAVIS['w']
     else:
@@ -174,7 +175,7 @@ def cpu_reference_rate(workload, seconds_budget=12.0, min_calls=3, max_calls=40)
         t0 = time.perf_counter()
         ref.match_memory(qk, qe)
         times.append(time.perf_counter() - t0)
-    scale = 1.0 if workload == 'davis5' else (17 * 120) / (LVOS['h'] * LVOS['w'])
+    scale = 1.0 if workload in ('davis5', 'davis_batch') else (17 * 120) / (LVOS['h'] * LVOS['w'])
     return scale / statistics.median(times), len(times), torch.get_num_threads()
 
 
@@ -183,7 +184,7 @@ def run_reference(args, rank):
         return
     rate, calls, threads = cpu_reference_rate(args.workload, seconds_budget=max(10.0, 0.5 * args.steps))
     sample = (f'{calls} match_memory calls of the oracle port (torch CPU fp32) on the {args.workload} workload, '
-              f'median call time' + ('' if args.workload == 'davis5' else '; 1/4 of the query rows, rate scaled'))
+              f'median call time' + ('' if args.workload != 'lvos_sharded' else '; 1/4 of the query rows, rate scaled'))
     line = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=calls, warmup=1,
                 ms_per_step=1000.0 / rate, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                 data='synthetic', impl='reference', config=workload_config(args.workload, args.gpus),
@@ -193,6 +194,12 @@ def run_reference(args, rank):
 
 
 def workload_config(workload, n_gpus):
+    if workload == 'davis_batch':
+        c = workload_config('davis5', n_gpus)
+        c.update(workload='davis2017_multiobject_readout_batched', sequences_per_gpu=BATCH,
+                 launch='one CUDA-graph replay per step; a step = one frame of each of the sequences (vosmem_match_batch)',
+                 parallelism=f'dp{n_gpus} x {BATCH} independent sequences per GPU')
+        return c
     if workload == 'davis5':
         return dict(workload='davis2017_multiobject_readout', hw=DAVIS['h'] * DAVIS['w'],
                     memory_elements=DAVIS['frames'] * DAVIS['h'] * DAVIS['w'], objects=DAVIS['n_obj'], ck=CK, cv=CV,
@@ -219,6 +226,7 @@ def run_ours(args, rank, world, local_rank):
     K, W = args.steps, args.warmup
     g = torch.Generator().manual_seed(1234 + 2 + rank)
     sharded = args.workload == 'lvos_sharded'
+    n_seq = 1
     if sharded:
         from vos_e_sam_b200.sharded import ShardedLongTermReadout
         h, w, n_obj = LVOS['h'], LVOS['w'], 1
@@ -230,19 +238,28 @@ def run_ours(args, rank, world, local_rank):
         n_mem = LVOS['n_long']
     else:
         h, w, n_obj = DAVIS['h'], DAVIS['w'], DAVIS['n_obj']
-        mgr = vos.MemoryManager(xmem_config(vosmem_value_dtype='bf16'))
-        fill_memory(mgr, g, h, w, DAVIS['frames'], n_obj, dev)
-        mgr.create_hidden_state(n_obj, torch.empty(1, CK, h, w, device=dev))
+        n_seq = BATCH if args.workload == 'davis_batch' else 1
+        mgrs = []
+        for _ in range(n_seq):
+            m = vos.MemoryManager(xmem_config(vosmem_value_dtype='bf16'))
+            fill_memory(m, g, h, w, DAVIS['frames'], n_obj, dev)
+            m.create_hidden_state(n_obj, torch.empty(1, CK, h, w, device=dev))
+            mgrs.append(m)
+        mgr = mgrs[0]
         n_mem = mgr.work_mem.size
     hw = h * w
     rows = n_obj * CV
 
     # a small pool of distinct query frames, host (pinned) and device copies
     pool = 4
-    host_q = [tuple(x.pin_memory() for x in synth.query(g, h, w)) for _ in range(pool)]
+    # pool entry = the query frames of one step: n_seq x (key, selection), one pinned host tensor each
+    host_q = [tuple(torch.stack(x).pin_memory() for x in zip(*[synth.query(g, h, w) for _ in range(n_seq)]))
+              for _ in range(pool)]                                   # each n_seq x 1 x CK x h x w
+    if n_seq == 1:
+        host_q = [(a[0], b[0]) for a, b in host_q]
     dev_q = [(a.to(dev), b.to(dev)) for a, b in host_q]
     flush = torch.empty(512 * 2 ** 20, dtype=torch.uint8, device=dev)
-    host_out = torch.empty((n_obj, CV, h, w), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((n_seq, n_obj, CV, h, w) if n_seq > 1 else (n_obj, CV, h, w), dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -258,16 +275,26 @@ def run_ours(args, rank, world, local_rank):
 
         from vos_e_sam_b200 import _native as N
 
+        def batch_problems(j):
+            """the object groups of one frame of every sequence, as one vosmem_match_batch problem list"""
+            qk, qe = dev_q[j]
+            return [p for m, k, e in zip(mgrs, qk, qe) for p in m._plan_match(k, e)[0]]
+
         def step(i, ev):
             qk, qe = dev_q[i % pool]
-            q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
+            q2, e2 = (qk.flatten(2)[0], qe.flatten(2)[0]) if n_seq == 1 else (None, None)
             flush.fill_(i & 0xFF)
             # the C call records ev[0..3] on the stream around its pack / select / readout kernels
             N.lib.vosmem_debug_set_stage_events(ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event, ev[3].cuda_event)
-            ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout
-            work.age()                                          # life_count += 1
+            if n_seq == 1:
+                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout
+                work.age()                                          # life_count += 1
+            else:
+                ops.match_batch(batch_problems(i % pool), TOP_K)
+                for m in mgrs:
+                    m.work_mem.age()
             ev[4].record()
-        launches_per_step = 3                                   # select_tc (packs its query tile), softmax_readout, age
+        launches_per_step = 2 + n_seq                           # select_tc (packs its query tiles), softmax_readout, age per store
     else:
         def step(i, ev):
             qk, qe = dev_q[i % pool]
@@ -287,18 +314,23 @@ def run_ours(args, rank, world, local_rank):
     graphs = None
     if not sharded:
         N.lib.vosmem_debug_set_stage_events(None, None, None, None)
-        graphs = []
+        graphs, graph_outputs = [], []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for j in range(pool):
-                qk, qe = dev_q[j]
-                q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
-                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)       # warm the workspace cache outside capture
+                if n_seq == 1:
+                    qk, qe = dev_q[j]
+                    q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
+                    run = lambda: (ops.match(q2, e2, seg, vals, rows, TOP_K, out=out), work.age())
+                else:
+                    probs = batch_problems(j)
+                    graph_outputs.append(probs)      # the captured kernels write these tensors on every replay
+                    run = lambda: (ops.match_batch(probs, TOP_K), [m.work_mem.age() for m in mgrs])
+                run()                                                    # warm the workspace cache outside capture
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=side):
-                    ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)
-                    work.age()
+                    run()
                 graphs.append(gr)
         torch.cuda.current_stream().wait_stream(side)
 
@@ -341,7 +373,12 @@ def run_ours(args, rank, world, local_rank):
         def e2e_step(i):
             a, b = host_q[i % pool]
             qk_d, qe_d = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
-            r = engine.match(qk_d, qe_d) if sharded else mgr.match_memory(qk_d, qe_d)
+            if sharded:
+                r = engine.match(qk_d, qe_d)
+            elif n_seq == 1:
+                r = mgr.match_memory(qk_d, qe_d)
+            else:
+                r = torch.stack(vos.match_memory_batch(mgrs, qk_d, qe_d))
             ready = torch.cuda.Event()
             ready.record()
             slot = i % 2
@@ -385,29 +422,29 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = stats.tolist()
-    frames = K if sharded else K * world       # sharded: all ranks cooperate on the same frames
+    frames = K if sharded else K * world * n_seq       # sharded: all ranks cooperate on the same frames
     value = frames / (total_ms / 1000.0)
-    e2e_value = (e2e_steps if sharded else e2e_steps * world) / (e2e_ms / 1000.0)
+    e2e_value = (e2e_steps if sharded else e2e_steps * world * n_seq) / (e2e_ms / 1000.0)
 
     if rank != 0:
         return
     pk = peaks()
     val_bytes = 2
     n_touch = min(n_mem, hw * TOP_K)
-    rd_bytes = rows * n_touch * val_bytes + rows * hw * 4 + hw * TOP_K * 12
+    rd_bytes = n_seq * (rows * n_touch * val_bytes + rows * hw * 4 + hw * TOP_K * 12)
     rd_t = statistics.mean(rd_ms) / 1000.0
-    sel_flops = 4.0 * n_mem * hw * CK
+    sel_flops = 4.0 * n_mem * hw * CK * n_seq
     sel_t = statistics.mean(sel_ms) / 1000.0
     if sharded:
         rd_bytes = rows * min(n_mem, hw * TOP_K) * val_bytes + rows * hw * 4 + hw * TOP_K * 12   # readout is replicated
         sel_flops /= world
     roof_rd = dict(kernel='softmax_readout_kernel (merge + softmax + usage + sparse readout)', bound='hbm', achieved=rd_bytes / rd_t / 1e9, peak=pk['hbm'], unit='GB/s',
-                   frac=rd_bytes / rd_t / 1e9 / pk['hbm'], traffic=ncu_traffic(args.workload, 'softmax_readout_kernel') if world == 1 else None,
+                   frac=rd_bytes / rd_t / 1e9 / pk['hbm'], traffic=ncu_traffic(args.workload, 'softmax_readout_kernel') if world == 1 and n_seq == 1 else None,
                    us_per_launch=rd_t * 1e6,
                    algorithmic_bytes=rd_bytes, peak_source=pk['source'])
     roof_sel = dict(kernel='select_tc_kernel', bound='tensor',
                     achieved=sel_flops / sel_t / 1e12, peak=pk['tflops'], unit='TFLOP/s',
-                    frac=sel_flops / sel_t / 1e12 / pk['tflops'], traffic=ncu_traffic(args.workload, 'select_tc_kernel') if world == 1 else None,
+                    frac=sel_flops / sel_t / 1e12 / pk['tflops'], traffic=ncu_traffic(args.workload, 'select_tc_kernel') if world == 1 and n_seq == 1 else None,
                     us_per_launch=sel_t * 1e6,
                     algorithmic_flops=sel_flops, executed_flop_multiplier=25.0 / 8.0, executed_frac=25.0 / 8.0 * sel_flops / sel_t / 1e12 / pk['tflops'], peak_source=pk['source'] + ', burst')
     dominant, other = (roof_rd, roof_sel) if rd_t >= sel_t else (roof_sel, roof_rd)
@@ -420,7 +457,7 @@ def run_ours(args, rank, world, local_rank):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                 ms_per_step=total_ms / K, higher_is_better=True, scaling='strong' if sharded else 'weak',
                 vs_baseline=None, dtype='bf16', data='synthetic', config=workload_config(args.workload, world),
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=2 * CK * hw * 4, d2h_bytes_per_step=rows * hw * 4),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n_seq * 2 * CK * hw * 4, d2h_bytes_per_step=n_seq * rows * hw * 4),
                 gpu_launches=K * launches_per_step, clocks=clocks.summary(), roofline=dominant,
                 roofline_other=other, cpu_baseline=cpu,
                 stage_us=dict(pack_query=statistics.mean(pack_ms) * 1e3, select=statistics.mean(sel_ms) * 1e3,
@@ -440,7 +477,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='davis5', choices=['davis5', 'lvos_sharded'])
+    ap.add_argument('--workload', default='davis5', choices=['davis5', 'davis_batch', 'lvos_sharded'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -46,6 +46,7 @@ enum vosmem_path {
 };
 
 #define VOSMEM_MAX_TOPK 32     /* per-query survivors held one per lane of a warp */
+#define VOSMEM_MAX_BATCH 12   /* problems per vosmem_match_batch call */
 #define VOSMEM_KEY_TILE 64     /* keys per packed image tile */
 #define VOSMEM_QUERY_TILE 128  /* queries per packed image tile (= TMEM lanes) */
 #define VOSMEM_MAX_SEGMENTS 2  /* [long-term | working] */
@@ -157,6 +158,16 @@ int vosmem_match(const vosmem_select_desc *select, const vosmem_readout_desc *re
 
 /* life_count[0:n] += 1  (kv_memory_store.py:99) */
 int vosmem_age(float *life_count, int64_t n, vosmem_stream_t stream);
+
+/* `n` (1..VOSMEM_MAX_BATCH) independent match problems -- e.g. one frame of each of n sequences, every one with its
+ * own MemoryManager (tools/runner.py:61-63 builds one tracker per sequence) -- in ONE selection launch and ONE
+ * readout launch (blockIdx.z = problem).  All problems share ck == 64, hw and top_k; memory sizes, segments, value
+ * rows and workspaces are per problem (the workspaces must be distinct).  With n x query tiles >= 148 every CTA
+ * streams a problem's whole key axis, which is where the tcgen05 path is most efficient.  Equivalent to n
+ * vosmem_match calls. */
+int vosmem_match_batch(const vosmem_select_desc *select, const vosmem_readout_desc *readout, int n,
+                       vosmem_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Dense twins of tracker/model/memory_util.py, for API parity (training-time read_memory,

@@ -367,6 +367,30 @@ def test_full_size_properties(vos):
     torch.testing.assert_close(r.view(2560, 1620), out, rtol=1e-5, atol=1e-5)
 
 
+def test_match_memory_batch_equals_individual_calls(vos):
+    """vosmem_match_batch (independent sequences in one selection + one readout launch, BASELINE configs[4]): three
+    managers of different memory sizes / object counts -- one of them with long-term memory and two object groups'
+    worth of rows -- against their own match_memory, readout and usage side effects alike."""
+    g = torch.Generator().manual_seed(77)
+    specs = [dict(n_frames=6, n_obj=2, n_long=0), dict(n_frames=9, n_obj=1, n_long=700), dict(n_frames=4, n_obj=3, n_long=0)]
+    pairs = []
+    for sp in specs:
+        state = g.get_state()
+        a, _ = build_manager(vos, g, (12, 20), sp['n_frames'], sp['n_obj'], 64, n_long=sp['n_long'], value_dtype='fp32')
+        g.set_state(state)
+        b, _ = build_manager(vos, g, (12, 20), sp['n_frames'], sp['n_obj'], 64, n_long=sp['n_long'], value_dtype='fp32')
+        pairs.append((a, b))
+    queries = [synth.query(g, 12, 20) for _ in specs]
+    want = [a.match_memory(qk.cuda(), qe.cuda()) for (a, _), (qk, qe) in zip(pairs, queries)]
+    got = vos.match_memory_batch([b for _, b in pairs], [qk.cuda() for qk, _ in queries], [qe.cuda() for _, qe in queries])
+    torch.cuda.synchronize()
+    for (a, b), w_, g_ in zip(pairs, want, got):
+        assert g_.shape == w_.shape
+        assert orc.rel_err(g_.cpu(), w_.cpu()) < 1e-3          # split counts differ -> candidate order / fp32 sums differ
+        assert orc.rel_err(b.work_mem.use_count.cpu(), a.work_mem.use_count.cpu()) < 1e-3
+        torch.testing.assert_close(b.work_mem.life_count, a.work_mem.life_count)
+
+
 def test_sharded_engine_single_rank_vs_oracle(vos):
     """ShardedLongTermReadout with world == 1 (CUDA backend, bf16 value shadow) == unsharded oracle readout."""
     from vos_e_sam_b200.sharded import ShardedLongTermReadout

@@ -15,7 +15,7 @@ Importing the package loads the shared library and fails loudly when it has not 
 import importlib
 
 _LAZY = {
-    'MemoryManager': 'memory_manager', 'KeyValueMemoryStore': 'kv_memory_store',
+    'MemoryManager': 'memory_manager', 'match_memory_batch': 'memory_manager', 'KeyValueMemoryStore': 'kv_memory_store',
     'get_similarity': 'memory_util', 'do_softmax': 'memory_util', 'get_affinity': 'memory_util', 'readout': 'memory_util',
 }
 __all__ = sorted(_LAZY)

@@ -15,6 +15,7 @@ OK = 0
 F32, BF16 = 0, 1
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 MAX_TOPK = 32
+MAX_BATCH = 12
 KEY_TILE = 64
 QUERY_TILE = 128
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     'vosmem_merge_topk': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     'vosmem_softmax_readout': (C.c_int, [C.POINTER(ReadoutDesc), vp, vp, vp]),
     'vosmem_match': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), vp, vp, vp]),
+    'vosmem_match_batch': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), C.c_int, vp]),
     'vosmem_age': (C.c_int, [vp, i64, vp]),
     'vosmem_similarity_dense': (C.c_int, [vp, i64, vp, vp, vp, C.c_int, i64, C.c_int, vp, vp]),
     'vosmem_softmax_dense': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, vp, i64, vp, vp]),

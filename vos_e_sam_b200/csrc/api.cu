@@ -21,12 +21,12 @@ void set_error(const char *fmt, ...) {
 
 // N-splits so that (query tiles x splits) fills the 148 SMs once (tcgen05: one CTA per SM) or gives the
 // SIMT kernel ~32 warps per SM; never fewer than ~4 key tiles per split.
-int choose_splits(int path, int hw, int64_t n_total) {
+int choose_splits(int path, int hw, int64_t n_total, int batch) {
   const int cap = splits_cap(hw);
   int64_t s;
   if (path == VOSMEM_PATH_TCGEN05) {
     int64_t n_qtiles = ceil_div64(hw, TQ);
-    s = 148 / n_qtiles;
+    s = 148 / (n_qtiles * batch);
     int64_t by_tiles = ceil_div64(n_total, TK) / 4;
     if (s > by_tiles) s = by_tiles;
   } else {
@@ -101,26 +101,38 @@ extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
   return carve_workspace(nullptr, ck, hw).bytes;
 }
 
-// pack the query, run the selection kernel: leaves the per-split candidate lists in the workspace
-static int run_selection(const vosmem_select_desc *d, cudaStream_t st, Workspace &ws, int &n_lists, int &n_pub) {
-  int rc = validate_select(d);
-  if (rc != VOSMEM_OK) return rc;
-  ws = carve_workspace(d->workspace, d->ck, d->hw);
-  int64_t total = 0;
-  for (int s = 0; s < d->n_segments; ++s) total += d->seg[s].end - d->seg[s].begin;
-  const int path = resolve_path(*d);
-  const int splits = choose_splits(path, d->hw, total);
+// run the selection kernel(s) of `n` problems: leaves the per-split candidate lists in each problem's workspace
+static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub) {
+  static std::atomic<uint32_t> epoch_counter{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count() | 1u};
+  int path = 0, splits = MAX_SPLITS;
+  for (int b = 0; b < n; ++b) {
+    int rc = validate_select(d + b);
+    if (rc != VOSMEM_OK) return rc;
+    ws[b] = carve_workspace(d[b].workspace, d[b].ck, d[b].hw);
+    ws[b].epoch = epoch_counter.fetch_add(1, std::memory_order_relaxed);   // tags this launch's published thresholds
+    int64_t total = 0;
+    for (int s = 0; s < d[b].n_segments; ++s) total += d[b].seg[s].end - d[b].seg[s].begin;
+    const int p = resolve_path(d[b]);
+    VOSMEM_CHECK_ARG(b == 0 || p == path, "match_batch: problems resolve to different kernel paths");
+    VOSMEM_CHECK_ARG(n == 1 || p == VOSMEM_PATH_TCGEN05, "match_batch: batches need the tcgen05 path (CK == 64, key images)");
+    VOSMEM_CHECK_ARG(d[b].hw == d[0].hw && d[b].top_k == d[0].top_k && d[b].ck == d[0].ck,
+                     "match_batch: problems must share CK, HW and top_k");
+    for (int o = 0; o < b; ++o)
+      VOSMEM_CHECK_ARG(d[o].workspace != d[b].workspace, "match_batch: problems %d and %d share a workspace", o, b);
+    path = p;
+    const int sp = choose_splits(p, d[b].hw, total, n);
+    splits = sp < splits ? sp : splits;
+  }
   n_lists = splits;                                                          // candidate lists left per query
   n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : splits;   // published threshold rows
-  static std::atomic<uint32_t> epoch_counter{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count() | 1u};
-  ws.epoch = epoch_counter.fetch_add(1, std::memory_order_relaxed);   // tags this launch's published thresholds (PubEntry)
   if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
+  int rc;
   if (path != VOSMEM_PATH_TCGEN05) {   // the tcgen05 kernel packs its query tile itself
-    rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws, st);
+    rc = launch_pack_query(d->query_key, d->query_selection, d->ck, d->hw, ws[0], st);
     if (rc != VOSMEM_OK) return rc;
   }
   if (g_stage_events[1]) cudaEventRecord(g_stage_events[1], st);
-  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(*d, ws, splits, st) : launch_select_simt(*d, ws, splits, st);
+  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(d, ws, n, splits, st) : launch_select_simt(*d, ws[0], splits, st);
   if (rc != VOSMEM_OK) return rc;
   if (g_stage_events[2]) cudaEventRecord(g_stage_events[2], st);
   return VOSMEM_OK;
@@ -132,7 +144,7 @@ extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score,
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
   int n_lists = 1, n_pub = 1;
-  int rc = run_selection(d, st, ws, n_lists, n_pub);
+  int rc = run_selection(d, 1, st, &ws, n_lists, n_pub);
   if (rc != VOSMEM_OK) return rc;
   rc = launch_merge_splits(ws, n_lists, n_pub, d->hw, d->top_k, d->index_base, out_score, out_index, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
@@ -140,7 +152,7 @@ extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score,
 }
 
 namespace vosmem {
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int n_lists, int n_pub, cudaStream_t st);
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int n, int n_lists, int n_pub, cudaStream_t st);
 }
 
 // One object group of match_memory: pack -> select -> (merge + softmax + usage + readout in one kernel).
@@ -157,9 +169,30 @@ extern "C" int vosmem_match(const vosmem_select_desc *select, const vosmem_reado
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
   int n_lists = 1, n_pub = 1;
-  int rc = run_selection(select, st, ws, n_lists, n_pub);
+  int rc = run_selection(select, 1, st, &ws, n_lists, n_pub);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_fused_readout(readout, ws, n_lists, n_pub, st);
+  rc = launch_fused_readout(readout, &ws, 1, n_lists, n_pub, st);
+  if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
+  return rc;
+}
+
+// n independent problems (sequences) in one selection launch + one readout launch (blockIdx.z = problem)
+extern "C" int vosmem_match_batch(const vosmem_select_desc *select, const vosmem_readout_desc *readout, int n,
+                                  vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(select && readout, "vosmem_match_batch: null descriptor array");
+  VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "vosmem_match_batch: n=%d outside [1, %d]", n, MAX_BATCH);
+  for (int b = 0; b < n; ++b) {
+    VOSMEM_CHECK_ARG(select[b].hw == readout[b].hw && select[b].top_k == readout[b].top_k,
+                     "vosmem_match_batch: problem %d: select (hw=%d, k=%d) and readout (hw=%d, k=%d) disagree", b,
+                     select[b].hw, select[b].top_k, readout[b].hw, readout[b].top_k);
+    VOSMEM_CHECK_ARG(select[b].index_base == 0, "vosmem_match_batch: index_base must be 0");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws[MAX_BATCH];
+  int n_lists = 1, n_pub = 1;
+  int rc = run_selection(select, n, st, ws, n_lists, n_pub);
+  if (rc != VOSMEM_OK) return rc;
+  rc = launch_fused_readout(readout, ws, n, n_lists, n_pub, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }

@@ -17,6 +17,7 @@ constexpr int KEY_TILE_BYTES = K8 * (TK / 8) * 128;    // 34816
 constexpr int QUERY_TILE_BYTES = K8 * (TQ / 8) * 128;  // 69632
 constexpr int CAND_SLOTS = 120;                 // per (split, query) candidate slots in the exchange buffer (2 x 60)
 constexpr int MAX_SPLITS = 32;
+constexpr int MAX_BATCH = VOSMEM_MAX_BATCH;      // independent problems (sequences) one launch can carry (blockIdx.z)
 constexpr int LISTS_PER_SPLIT = 2;              // the tcgen05 kernel publishes two thresholds per (split, query)
 
 void set_error(const char *fmt, ...);
@@ -209,9 +210,9 @@ struct SelectPlan {
 
 int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st);
 int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
-int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
+int launch_select_tc(const vosmem_select_desc *d, const Workspace *ws, int n, int splits, cudaStream_t st);
 int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st);
-int choose_splits(int path, int hw, int64_t n_total);
+int choose_splits(int path, int hw, int64_t n_total, int batch = 1);
 
 }  // namespace vosmem

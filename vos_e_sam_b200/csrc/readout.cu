@@ -37,6 +37,11 @@ struct ReadoutArgs {
   float *out_weight;
 };
 
+struct ReadoutBatch {   // kernel parameter: one ReadoutArgs per problem (blockIdx.z)
+  ReadoutArgs p[MAX_BATCH];
+};
+static_assert(sizeof(ReadoutBatch) <= 3584, "kernel parameter space");
+
 template <typename T, int VEC>
 struct Loader;
 template <>
@@ -128,7 +133,8 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
 
 // grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
 template <typename T, int VEC, int RQ, bool FUSED>
-__global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(ReadoutArgs a) {
+__global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __grid_constant__ ReadoutBatch batch) {
+  const ReadoutArgs &a = batch.p[blockIdx.z];
   constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering one pass of channels
   constexpr int GROUPS = RTHREADS / TPQ;                             // query groups working concurrently
   constexpr int CH_PER_PASS = TPQ * VEC;                             // <= RCH
@@ -196,14 +202,19 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(ReadoutArg
 
 
 template <int RQ, bool FUSED>
-int launch(const ReadoutArgs &a, int value_dtype, bool vec_ok, cudaStream_t st) {
-  dim3 grid((a.hw + RQ - 1) / RQ, FUSED ? 1 : (a.rows + RCH - 1) / RCH);
+int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStream_t st) {
+  int hw = 0, rows = 0;
+  for (int i = 0; i < n; ++i) {
+    hw = b.p[i].hw > hw ? b.p[i].hw : hw;
+    rows = b.p[i].rows > rows ? b.p[i].rows : rows;
+  }
+  dim3 grid((hw + RQ - 1) / RQ, FUSED ? 1 : (rows + RCH - 1) / RCH, n);
   if (value_dtype == VOSMEM_F32) {
-    if (vec_ok) softmax_readout_kernel<float, 4, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
-    else softmax_readout_kernel<float, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+    if (vec_ok) softmax_readout_kernel<float, 4, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
+    else softmax_readout_kernel<float, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
   } else {
-    if (vec_ok) softmax_readout_kernel<__nv_bfloat16, 8, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
-    else softmax_readout_kernel<__nv_bfloat16, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(a);
+    if (vec_ok) softmax_readout_kernel<__nv_bfloat16, 8, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
+    else softmax_readout_kernel<__nv_bfloat16, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
   }
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
@@ -241,14 +252,20 @@ int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
 
 }  // namespace
 
-// fused front end, used by vosmem_match after the selection kernel
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace &ws, int n_lists, int n_pub, cudaStream_t st) {
-  ReadoutArgs a{};
-  bool vec_ok;
-  int rc = fill_args(d, a, vec_ok);
-  if (rc != VOSMEM_OK) return rc;
-  a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(d->hw, TQ), ws.epoch};
-  return launch<4, true>(a, d->value_dtype, vec_ok, st);
+// fused front end, used by vosmem_match / vosmem_match_batch after the selection kernel
+int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int n, int n_lists, int n_pub, cudaStream_t st) {
+  VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "readout: batch of %d problems outside [1, %d]", n, MAX_BATCH);
+  ReadoutBatch b{};
+  bool vec_all = true;
+  for (int i = 0; i < n; ++i) {
+    bool vec_ok;
+    int rc = fill_args(d + i, b.p[i], vec_ok);
+    if (rc != VOSMEM_OK) return rc;
+    VOSMEM_CHECK_ARG(d[i].value_dtype == d[0].value_dtype, "readout: problems of one batch must share the value storage type");
+    vec_all = vec_all && vec_ok;
+    b.p[i].lists = SplitLists{ws[i].cand, ws[i].cand_count, ws[i].pub, n_lists, n_pub, (int)round_up64(d[i].hw, TQ), ws[i].epoch};
+  }
+  return launch<4, true>(b, n, d[0].value_dtype, vec_all, st);
 }
 
 }  // namespace vosmem
@@ -258,11 +275,12 @@ using namespace vosmem;
 extern "C" int vosmem_softmax_readout(const vosmem_readout_desc *d, const float *score, const int64_t *index,
                                       vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(score && index, "vosmem_softmax_readout: null candidate lists");
-  ReadoutArgs a{};
+  ReadoutBatch b{};
+  ReadoutArgs &a = b.p[0];
   bool vec_ok;
   int rc = fill_args(d, a, vec_ok);
   if (rc != VOSMEM_OK) return rc;
   a.score = score;
   a.index = index;
-  return launch<8, false>(a, d->value_dtype, vec_ok, (cudaStream_t)stream);
+  return launch<8, false>(b, 1, d->value_dtype, vec_ok, (cudaStream_t)stream);
 }

@@ -96,6 +96,11 @@ struct TcArgs {
   long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
 };
 
+struct TcBatch {   // kernel parameter: one TcArgs per problem (blockIdx.z)
+  TcArgs p[MAX_BATCH];
+};
+static_assert(sizeof(TcBatch) <= 3584, "kernel parameter space");
+
 // The query operand lives in tensor memory: 8 columns per K=16 step, [hi steps 0-7 | lo steps 0-7 | tail].
 // One tcgen05.cp (128 rows x 256 bits) per step from the packed shared-memory image.
 __device__ __forceinline__ void stage_query_in_tmem(uint32_t q_base, uint32_t tmem_a) {
@@ -322,7 +327,8 @@ __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsi
 }
 
 template <int R>   // R = tracked / published rank per virtual split (see "Thresholds")
-__global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_constant__ TcBatch batch) {
+  const TcArgs &a = batch.p[blockIdx.z];
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + SM_BAR);
   uint64_t *bar_empty = bar_full + STAGES;
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const TcArgs a
   const int64_t g_lo = a.tiles_total * blockIdx.y / a.splits;
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
   const int n_tiles = (int)(g_hi - g_lo);
-  long long *dbg = a.dbg ? a.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  long long *dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 : nullptr;
   const long long t_entry = clock64();
   unsigned long long g_entry = 0;
   if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
@@ -728,36 +734,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_tile_kernel(const unsigned
 
 long long *g_tc_debug = nullptr;  // set through vosmem_debug_set_timing_buffer
 
-int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st) {
-  VOSMEM_CHECK_ARG(d.ck == CK_TC, "select(tcgen05): CK must be 64 (got %d)", d.ck);
-  TcArgs a{};
-  int64_t tiles = 0;
-  for (int s = 0; s < 2; ++s) {
-    if (s < d.n_segments) {
-      const vosmem_segment &g = d.seg[s];
-      VOSMEM_CHECK_ARG(g.key_image != nullptr || g.end == g.begin, "select(tcgen05): segment %d has no key image", s);
-      TcSeg &t = a.seg[s];
-      t.image = static_cast<const unsigned char *>(g.key_image);
-      t.begin = g.begin;
-      t.end = g.end;
-      t.tile0 = g.begin / TK;
-      t.tiles = g.end > g.begin ? ceil_div64(g.end, TK) - t.tile0 : 0;
-      if (s == 0) a.len0 = g.end - g.begin;
-      tiles += t.tiles;
+int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, cudaStream_t st) {
+  VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "select(tcgen05): batch of %d problems outside [1, %d]", n, MAX_BATCH);
+  TcBatch batch{};
+  for (int b = 0; b < n; ++b) {
+    const vosmem_select_desc &d = descs[b];
+    const Workspace &ws = wss[b];
+    VOSMEM_CHECK_ARG(d.ck == CK_TC, "select(tcgen05): CK must be 64 (got %d)", d.ck);
+    VOSMEM_CHECK_ARG(d.hw == descs[0].hw, "select(tcgen05): problems of one batch must share HW (%d vs %d)", d.hw, descs[0].hw);
+    TcArgs &a = batch.p[b];
+    int64_t tiles = 0;
+    for (int s = 0; s < 2; ++s) {
+      if (s < d.n_segments) {
+        const vosmem_segment &g = d.seg[s];
+        VOSMEM_CHECK_ARG(g.key_image != nullptr || g.end == g.begin, "select(tcgen05): segment %d has no key image", s);
+        TcSeg &t = a.seg[s];
+        t.image = static_cast<const unsigned char *>(g.key_image);
+        t.begin = g.begin;
+        t.end = g.end;
+        t.tile0 = g.begin / TK;
+        t.tiles = g.end > g.begin ? ceil_div64(g.end, TK) - t.tile0 : 0;
+        if (s == 0) a.len0 = g.end - g.begin;
+        tiles += t.tiles;
+      }
     }
+    a.tiles_total = tiles;
+    a.hw = d.hw;
+    a.hw_pad = (int)round_up64(d.hw, TQ);
+    a.splits = splits;
+    a.qk = d.query_key;
+    a.qe = d.query_selection;
+    a.pub = ws.pub;
+    a.epoch = ws.epoch;
+    a.cand = ws.cand;
+    a.cand_count = ws.cand_count;
+    a.dbg = g_tc_debug;
   }
-  a.tiles_total = tiles;
-  a.hw = d.hw;
-  a.hw_pad = (int)round_up64(d.hw, TQ);
-  a.splits = splits;
-  a.qk = d.query_key;
-  a.qe = d.query_selection;
-  a.pub = ws.pub;
-  a.epoch = ws.epoch;
-  a.cand = ws.cand;
-  a.cand_count = ws.cand_count;
-  a.dbg = g_tc_debug;
-  dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits);
+  const vosmem_select_desc &d = descs[0];
+  dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits, n);
   // R * (virtual splits) >= 33 keys must stand behind a shared threshold
   const int r = (33 + HALVES * splits - 1) / (HALVES * splits);
 #define VOSMEM_LAUNCH_TC(RR)                                                                                     \
@@ -767,7 +781,7 @@ int launch_select_tc(const vosmem_select_desc &d, const Workspace &ws, int split
       VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    select_tc_kernel<RR><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);                                                 \
+    select_tc_kernel<RR><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                                 \
   } while (0)
   if (r <= 1) VOSMEM_LAUNCH_TC(1);
   else if (r == 2) VOSMEM_LAUNCH_TC(2);

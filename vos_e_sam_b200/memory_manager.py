@@ -84,8 +84,9 @@ class MemoryManager:
         return ops.readout_dense(flat, affinity[0]).view(n_obj, cv, -1)
 
     # ------------------------------------------------------------------------------------------------
-    def match_memory(self, query_key, selection):
-        """query_key, selection: B x CK x H x W (B == 1)  ->  num_objects x CV x H x W  (memory_manager.py:57-150)."""
+    def _plan_match(self, query_key, selection):
+        """The object groups of one match_memory call as independent problems (ops.MatchProblem), the output they
+        fill, and the stores whose life_count grows afterwards."""
         work = self.work_mem
         num_groups = work.num_groups
         h, w = query_key.shape[-2:]
@@ -105,10 +106,8 @@ class MemoryManager:
 
         rows_total = sum(work.group_rows(gi) for gi in range(num_groups))
         out = torch.empty((rows_total, hw), dtype=torch.float32, device=qk.device)
-        if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != qk.device:
-            self._scratch = (torch.empty((hw, self.top_k), dtype=torch.float32, device=qk.device),
-                             torch.empty((hw, self.top_k), dtype=torch.int64, device=qk.device))
 
+        problems = []
         row0 = 0
         for gi in range(num_groups):
             segments, values = [], []
@@ -124,17 +123,25 @@ class MemoryManager:
             values.append(work.value_segment(gi, first, with_usage=(gi == 0 and track_work),
                                              usage_offset=n_work - len_w))
             rows = work.group_rows(gi)
-            ops.match(qk, qe, segments, values, rows, self.top_k, out=out[row0:row0 + rows], path=self.path,
-                      scratch=self._scratch)
+            problems.append(ops.MatchProblem(qk, qe, segments, values, rows, out[row0:row0 + rows]))
             row0 += rows
+        aging = ([work] if track_work else []) + ([long] if track_long else [])
+        return problems, out.view(rows_total // self.CV, self.CV, h, w), aging
 
+    def match_memory(self, query_key, selection):
+        """query_key, selection: B x CK x H x W (B == 1)  ->  num_objects x CV x H x W  (memory_manager.py:57-150)."""
+        problems, out, aging = self._plan_match(query_key, selection)
+        hw = out.shape[-2] * out.shape[-1]
+        if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != out.device:
+            self._scratch = (torch.empty((hw, self.top_k), dtype=torch.float32, device=out.device),
+                             torch.empty((hw, self.top_k), dtype=torch.int64, device=out.device))
+        for p in problems:
+            ops.match(p.qk, p.qe, p.segments, p.values, p.rows, self.top_k, out=p.out, path=self.path,
+                      scratch=self._scratch)
         # life_count += 1 on every store whose usage was recorded (kv_memory_store.py:99)
-        if track_work:
-            work.age()
-        if track_long:
-            long.age()
-
-        return out.view(rows_total // self.CV, self.CV, h, w)
+        for store in aging:
+            store.age()
+        return out
 
     # ------------------------------------------------------------------------------------------------
     def add_memory(self, key, shrinkage, value, objects, selection=None):
@@ -236,3 +243,26 @@ class MemoryManager:
         prototype_shrinkage = (self._readout(affinity[0], candidate_shrinkage)
                                if candidate_shrinkage is not None else None)
         return prototype_key, prototype_value, prototype_shrinkage
+
+
+def match_memory_batch(managers, query_keys, selections):
+    """``[m.match_memory(k, e) for m, k, e in zip(managers, query_keys, selections)]`` for INDEPENDENT managers (one
+    per sequence: tools/runner.py:61-63), with the selection and readout kernels of all of them launched together
+    (``vosmem_match_batch``: blockIdx.z = problem).  Managers must share CK == 64, the query size and top_k; anything
+    else falls back to one call per manager."""
+    managers = list(managers)
+    plans = [m._plan_match(k, e) for m, k, e in zip(managers, query_keys, selections)]
+    top_k = managers[0].top_k
+    hw = plans[0][1].shape[-2] * plans[0][1].shape[-1]
+    same = all(m.top_k == top_k and m.CK == 64 and m.path != N.PATH_SIMT for m in managers) and \
+        all(o.shape[-2] * o.shape[-1] == hw for _, o, _ in plans)
+    if same and len(set(map(id, managers))) == len(managers):
+        ops.match_batch([p for probs, _, _ in plans for p in probs], top_k)
+    else:
+        for m, (probs, out, _) in zip(managers, plans):
+            for p in probs:
+                ops.match(p.qk, p.qe, p.segments, p.values, p.rows, m.top_k, out=p.out, path=m.path)
+    for _, _, aging in plans:
+        for store in aging:
+            store.age()
+    return [out for _, out, _ in plans]

@@ -64,11 +64,12 @@ class ValueSegment:
     use_count: Optional[Tensor] = None   # flat fp32, element i <-> shadow row i
 
 
-_workspaces: Dict[Tuple[int, int, int], Tensor] = {}
+_workspaces: Dict[Tuple[int, int, int, int], Tensor] = {}
 
 
-def workspace_for(device: torch.device, ck: int, hw: int) -> Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), ck, hw)
+def workspace_for(device: torch.device, ck: int, hw: int, slot: int = 0) -> Tensor:
+    """Cached per-(device, shape) scratch; `slot` gives the problems of one batch distinct workspaces."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), ck, hw, slot)
     ws = _workspaces.get(key)
     if ws is None:
         nbytes = N.lib.vosmem_workspace_bytes(ck, hw, 0)
@@ -111,7 +112,7 @@ def age(life_count: Tensor, n: int) -> None:
 
 # ------------------------------------------------------------------------------------------------
 def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment], top_k: int, index_base: int,
-                 path: int, keep: list) -> N.SelectDesc:
+                 path: int, keep: list, slot: int = 0, d: Optional[N.SelectDesc] = None) -> N.SelectDesc:
     _need(qk, 'query_key')
     ck, hw = qk.shape
     qk = qk.contiguous()
@@ -119,7 +120,7 @@ def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment
     if qe is not None:
         qe = _need(qe, 'query_selection').contiguous()
         keep.append(qe)
-    d = N.SelectDesc()
+    d = N.SelectDesc() if d is None else d
     d.ck, d.hw, d.top_k = ck, hw, top_k
     d.query_key, d.query_selection = qk.data_ptr(), _p(qe)
     d.n_segments = len(segments)
@@ -137,7 +138,7 @@ def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment
         g.begin, g.end = s.begin, s.end
     d.index_base = index_base
     d.path = path
-    ws = workspace_for(qk.device, ck, hw)
+    ws = workspace_for(qk.device, ck, hw, slot)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     return d
 
@@ -167,8 +168,8 @@ def merge_topk(scores: Tensor, indices: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def _readout_desc(hw: int, top_k: int, rows: int, values: Sequence[ValueSegment], out: Tensor,
-                  out_weight: Optional[Tensor]) -> N.ReadoutDesc:
-    d = N.ReadoutDesc()
+                  out_weight: Optional[Tensor], d: Optional[N.ReadoutDesc] = None) -> N.ReadoutDesc:
+    d = N.ReadoutDesc() if d is None else d
     d.hw, d.top_k, d.rows = hw, top_k, rows
     d.value_dtype = DTYPE_CODE[values[0].shadow.dtype]
     d.n_segments = len(values)
@@ -216,6 +217,36 @@ def match(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment], valu
     check(N.lib.vosmem_match(C.byref(sd), C.byref(rd), scratch[0].data_ptr(), scratch[1].data_ptr(), _stream()),
           'vosmem_match')
     return out
+
+
+@dataclass
+class MatchProblem:
+    """One entry of match_batch: what ops.match takes, for one sequence / object group."""
+    qk: Tensor
+    qe: Optional[Tensor]
+    segments: Sequence[KeySegment]
+    values: Sequence[ValueSegment]
+    rows: int
+    out: Optional[Tensor] = None
+
+
+def match_batch(problems: Sequence[MatchProblem], top_k: int) -> List[Tensor]:
+    """Independent match problems (same CK == 64, HW and top_k; e.g. one frame of each of several sequences) in one
+    selection launch and one readout launch per chunk of N.MAX_BATCH.  Returns the outputs (rows_i x HW)."""
+    outs: List[Tensor] = []
+    for c0 in range(0, len(problems), N.MAX_BATCH):
+        chunk = problems[c0:c0 + N.MAX_BATCH]
+        n = len(chunk)
+        keep: list = []
+        sds = (N.SelectDesc * n)()
+        rds = (N.ReadoutDesc * n)()
+        for i, p in enumerate(chunk):
+            _select_desc(p.qk, p.qe, p.segments, top_k, 0, N.PATH_TCGEN05, keep, slot=i, d=sds[i])
+            out = p.out if p.out is not None else torch.empty((p.rows, sds[i].hw), dtype=torch.float32, device=p.qk.device)
+            _readout_desc(sds[i].hw, top_k, p.rows, p.values, out, None, d=rds[i])
+            outs.append(out)
+        check(N.lib.vosmem_match_batch(sds, rds, n, _stream()), 'vosmem_match_batch')
+    return outs
 
 
 # ------------------------------------------------------------------------------------------------
