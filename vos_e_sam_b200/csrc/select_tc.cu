@@ -261,6 +261,29 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
   return st;
 }
 
+// One pass of the refresher warp over the published rows: NB x 4 independent 8-byte loads in flight per lane.  Rows
+// past the end re-read the last row (harmless for a minimum), so there is no branch between the loads and they are
+// all issued before the first use.
+template <int NB>
+__device__ __forceinline__ void refresh_pass(const PubEntry *pub_row, int vsplits, int hw_pad, uint32_t epoch,
+                                             float (&m)[TQ / 32]) {
+  for (int y0 = 0; y0 < vsplits; y0 += NB) {
+    uint2 raw[NB][TQ / 32];
+#pragma unroll
+    for (int y = 0; y < NB; ++y) {
+      const int yy = min(y0 + y, vsplits - 1);
+#pragma unroll
+      for (int h = 0; h < TQ / 32; ++h)
+        raw[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub_row + (int64_t)yy * hw_pad + 32 * h));
+    }
+#pragma unroll
+    for (int y = 0; y < NB; ++y)
+#pragma unroll
+      for (int h = 0; h < TQ / 32; ++h)
+        m[h] = fminf(m[h], raw[y][h].y == epoch ? __uint_as_float(raw[y][h].x) : -INFINITY);
+  }
+}
+
 // Warps 0-7 (256 threads): the query operand of this CTA's 128 queries, written in place as the shared-memory image
 // the tcgen05.cp copies expect.  Row y[q] = [-e | 2 q e | -sum_c e q^2] (memory_util.py:20-27; e = 1 and no last term
 // when there is no selection, :28-32), every fp32 entry as a bf16 (hi, lo) pair; 16-byte chunk order per row:
@@ -380,32 +403,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       float m[TQ / 32];
 #pragma unroll
       for (int h = 0; h < TQ / 32; ++h) m[h] = INFINITY;
-      for (int y0 = 0; y0 < vsplits; y0 += RB) {
-        // RB x 4 independent 8-byte loads in flight per lane: rows past the end re-read the last row (harmless for a
-        // minimum), so there is no branch between the loads and they are all issued before the first use
-        uint2 raw[RB][TQ / 32];
-#pragma unroll
-        for (int y = 0; y < RB; ++y) {
-          const int yy = min(y0 + y, vsplits - 1);
-#pragma unroll
-          for (int h = 0; h < TQ / 32; ++h)
-            raw[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub_row + (int64_t)yy * a.hw_pad + 32 * h));
-        }
-#pragma unroll
-        for (int y = 0; y < RB; ++y)
-#pragma unroll
-          for (int h = 0; h < TQ / 32; ++h)
-            m[h] = fminf(m[h], raw[y][h].y == a.epoch ? __uint_as_float(raw[y][h].x) : -INFINITY);
-      }
+      // rows per batch sized to the number of virtual splits (2: one CTA per query tile, e.g. batched sequences;
+      // 4: two splits, LVOS-size query counts; else 11 at a time), so that no pass re-reads rows for nothing
+      if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, a.epoch, m);
+      else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, a.epoch, m);
+      else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, a.epoch, m);
 #pragma unroll
       for (int h = 0; h < TQ / 32; ++h) tau_sh[lane + 32 * h] = m[h];
-      if (dbg) {
-        bool all_ok = true;
-#pragma unroll
-        for (int h = 0; h < TQ / 32; ++h) all_ok = all_ok && m[h] != -INFINITY;
-        if (__all_sync(FULL, all_ok) && dbg[26] == 0 && lane == 0) { dbg[26] = clock64() - t_entry; dbg[27] = it; }
-        if (it == 0 && lane == 0) dbg[28] = clock64() - t_entry;
-      }
       if (it >= 16) __nanosleep(256);   // thresholds move fastest during the first tiles
     }
   } else if (warp == W_PRODUCER) {
@@ -554,7 +558,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         st.pub = best[R - 1];
         pub_store(pub_mine + lane, st.pub, a.epoch);
       }
-      if (dbg && n_done == 0 && lane == 0 && quarter == 1 && half == 0) dbg[25] = clock64() - t_entry;
       if (R <= 3 && n_done == 0) {
         // First tile of this set with many splits: nothing is known yet and every score would be kept.  The tile
         // sits in registers, so give the other splits a bounded moment to publish their first values (the MMA warp
