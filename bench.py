@@ -287,14 +287,11 @@ def run_ours(args, rank, world, local_rank):
             # the C call records ev[0..3] on the stream around its pack / select / readout kernels
             N.lib.vosmem_debug_set_stage_events(ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event, ev[3].cuda_event)
             if n_seq == 1:
-                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout
-                work.age()                                          # life_count += 1
+                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout(+age)
             else:
                 ops.match_batch(batch_problems(i % pool), TOP_K)
-                for m in mgrs:
-                    m.work_mem.age()
             ev[4].record()
-        launches_per_step = 2 + n_seq                           # select_tc (packs its query tiles), softmax_readout, age per store
+        launches_per_step = 2                                   # select_tc (packs its query tiles), softmax_readout (ages life_count)
     else:
         def step(i, ev):
             qk, qe = dev_q[i % pool]
@@ -322,11 +319,11 @@ def run_ours(args, rank, world, local_rank):
                 if n_seq == 1:
                     qk, qe = dev_q[j]
                     q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
-                    run = lambda: (ops.match(q2, e2, seg, vals, rows, TOP_K, out=out), work.age())
+                    run = lambda: ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)
                 else:
                     probs = batch_problems(j)
                     graph_outputs.append(probs)      # the captured kernels write these tensors on every replay
-                    run = lambda: (ops.match_batch(probs, TOP_K), [m.work_mem.age() for m in mgrs])
+                    run = lambda: ops.match_batch(probs, TOP_K)
                 run()                                                    # warm the workspace cache outside capture
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=side):

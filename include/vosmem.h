@@ -132,6 +132,8 @@ typedef struct vosmem_value_segment {
   int64_t first;        /* global candidate index of shadow row 0                               */
   int64_t count;        /* candidates [first, first+count) live in this shadow                  */
   float *use_count;     /* += sum_q affinity[n, q]   or NULL (kv_memory_store.py:92-99)         */
+  float *life_count;    /* [0, count) += 1 in the same launch, or NULL (kv_memory_store.py:99;   */
+                        /* otherwise call vosmem_age)                                            */
 } vosmem_value_segment;
 
 typedef struct vosmem_readout_desc {

@@ -47,8 +47,8 @@ def test_struct_layouts_match_the_header(native):
     # sizes follow from the C declaration order (int / pointer / int64 with natural alignment)
     assert ctypes.sizeof(native.Segment) == 48
     assert ctypes.sizeof(native.SelectDesc) == 16 + 16 + 8 + 2 * 48 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(native.ValueSegment) == 40
-    assert ctypes.sizeof(native.ReadoutDesc) == 24 + 2 * 40 + 24
+    assert ctypes.sizeof(native.ValueSegment) == 48
+    assert ctypes.sizeof(native.ReadoutDesc) == 24 + 2 * 48 + 24
 
 
 def test_host_side_layout_helpers(native):

@@ -34,7 +34,7 @@ class SelectDesc(C.Structure):
 
 
 class ValueSegment(C.Structure):
-    _fields_ = [('shadow', vp), ('shadow_ld', i64), ('first', i64), ('count', i64), ('use_count', vp)]
+    _fields_ = [('shadow', vp), ('shadow_ld', i64), ('first', i64), ('count', i64), ('use_count', vp), ('life_count', vp)]
 
 
 class ReadoutDesc(C.Structure):

@@ -27,6 +27,7 @@ struct ReadoutArgs {
   int64_t shadow_ld[2];
   int64_t first[2], count[2];
   float *use_count[2];
+  float *life_count[2];
   int n_segments;
   int hw, top_k, rows;
   const float *score;      // staged front end
@@ -149,6 +150,15 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
   const int q0 = blockIdx.x * RQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // --- life_count += 1 over the segments' elements (kv_memory_store.py:99), spread over the CTAs of the first chunk
+  if (blockIdx.y == 0) {
+#pragma unroll
+    for (int sgi = 0; sgi < 2; ++sgi)
+      if (sgi < a.n_segments && a.life_count[sgi])
+        for (int64_t i = (int64_t)blockIdx.x * RTHREADS + threadIdx.x; i < a.count[sgi]; i += (int64_t)gridDim.x * RTHREADS)
+          a.life_count[sgi][i] += 1.0f;
+  }
+
   // --- per query (one warp each): survivors -> softmax weights -> value rows ---
   for (int qq = warp; qq < RQ; qq += RTHREADS / 32)
     resolve_query<T, FUSED>(a, q0 + qq, blockIdx.y == 0, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane, s_w[qq], s_row[qq],
@@ -237,6 +247,7 @@ int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
     a.first[s] = g.first;
     a.count[s] = g.count;
     a.use_count[s] = g.use_count;
+    a.life_count[s] = g.life_count;
     vec_ok = vec_ok && (g.shadow_ld % vec == 0) && (reinterpret_cast<uintptr_t>(g.shadow) % 16 == 0);
   }
   vec_ok = vec_ok && (d->rows % vec == 0);

@@ -321,8 +321,10 @@ class KeyValueMemoryStore:
 
     def value_segment(self, gi: int, first: int, with_usage: bool, usage_offset: int = 0) -> ops.ValueSegment:
         vg = self._groups[gi]
-        use = self._use.buf.view(-1)[usage_offset:] if (with_usage and self.count_usage) else None
-        return ops.ValueSegment(shadow=vg.shadow, first=first, count=vg.n, use_count=use)
+        track = with_usage and self.count_usage
+        use = self._use.buf.view(-1)[usage_offset:] if track else None
+        life = self._life.buf.view(-1)[usage_offset:] if track else None     # aged by the same readout launch
+        return ops.ValueSegment(shadow=vg.shadow, first=first, count=vg.n, use_count=use, life_count=life)
 
     def group_rows(self, gi: int) -> int:
         return self._groups[gi].rows

@@ -85,8 +85,8 @@ class MemoryManager:
 
     # ------------------------------------------------------------------------------------------------
     def _plan_match(self, query_key, selection):
-        """The object groups of one match_memory call as independent problems (ops.MatchProblem), the output they
-        fill, and the stores whose life_count grows afterwards."""
+        """The object groups of one match_memory call as independent problems (ops.MatchProblem) and the output they
+        fill."""
         work = self.work_mem
         num_groups = work.num_groups
         h, w = query_key.shape[-2:]
@@ -125,22 +125,25 @@ class MemoryManager:
             rows = work.group_rows(gi)
             problems.append(ops.MatchProblem(qk, qe, segments, values, rows, out[row0:row0 + rows]))
             row0 += rows
-        aging = ([work] if track_work else []) + ([long] if track_long else [])
-        return problems, out.view(rows_total // self.CV, self.CV, h, w), aging
+        # life_count += 1 on every store whose usage is recorded (kv_memory_store.py:99) happens inside group 0's
+        # readout launch (ValueSegment.life_count), so nothing is left to do after the kernels
+        return problems, out.view(rows_total // self.CV, self.CV, h, w)
 
     def match_memory(self, query_key, selection):
         """query_key, selection: B x CK x H x W (B == 1)  ->  num_objects x CV x H x W  (memory_manager.py:57-150)."""
-        problems, out, aging = self._plan_match(query_key, selection)
+        problems, out = self._plan_match(query_key, selection)
         hw = out.shape[-2] * out.shape[-1]
         if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != out.device:
             self._scratch = (torch.empty((hw, self.top_k), dtype=torch.float32, device=out.device),
                              torch.empty((hw, self.top_k), dtype=torch.int64, device=out.device))
+        if len(problems) > 1 and self.CK == 64 and self.path != N.PATH_SIMT:
+            # several object groups (objects that appeared in different frames): same query, different key suffixes --
+            # one selection launch and one readout launch for all of them
+            ops.match_batch(problems, self.top_k)
+            return out
         for p in problems:
             ops.match(p.qk, p.qe, p.segments, p.values, p.rows, self.top_k, out=p.out, path=self.path,
                       scratch=self._scratch)
-        # life_count += 1 on every store whose usage was recorded (kv_memory_store.py:99)
-        for store in aging:
-            store.age()
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -255,14 +258,11 @@ def match_memory_batch(managers, query_keys, selections):
     top_k = managers[0].top_k
     hw = plans[0][1].shape[-2] * plans[0][1].shape[-1]
     same = all(m.top_k == top_k and m.CK == 64 and m.path != N.PATH_SIMT for m in managers) and \
-        all(o.shape[-2] * o.shape[-1] == hw for _, o, _ in plans)
+        all(o.shape[-2] * o.shape[-1] == hw for _, o in plans)
     if same and len(set(map(id, managers))) == len(managers):
-        ops.match_batch([p for probs, _, _ in plans for p in probs], top_k)
+        ops.match_batch([p for probs, _ in plans for p in probs], top_k)
     else:
-        for m, (probs, out, _) in zip(managers, plans):
+        for m, (probs, out) in zip(managers, plans):
             for p in probs:
                 ops.match(p.qk, p.qe, p.segments, p.values, p.rows, m.top_k, out=p.out, path=m.path)
-    for _, _, aging in plans:
-        for store in aging:
-            store.age()
-    return [out for _, out, _ in plans]
+    return [out for _, out in plans]

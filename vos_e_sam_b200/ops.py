@@ -62,6 +62,7 @@ class ValueSegment:
     first: int
     count: int
     use_count: Optional[Tensor] = None   # flat fp32, element i <-> shadow row i
+    life_count: Optional[Tensor] = None  # flat fp32; [0, count) += 1 inside the readout launch when given
 
 
 _workspaces: Dict[Tuple[int, int, int, int], Tensor] = {}
@@ -180,6 +181,7 @@ def _readout_desc(hw: int, top_k: int, rows: int, values: Sequence[ValueSegment]
         g.shadow, g.shadow_ld = v.shadow.data_ptr(), v.shadow.stride(0)
         g.first, g.count = v.first, v.count
         g.use_count = _p(v.use_count)
+        g.life_count = _p(v.life_count)
     assert out.dim() == 2 and out.shape == (rows, hw) and out.stride(1) == 1
     d.out, d.out_ld = out.data_ptr(), out.stride(0)
     d.out_weight = _p(out_weight)
