@@ -36,6 +36,7 @@ import torch  # noqa: E402
 
 CK, CV, TOP_K = 64, 512, 30
 DAVIS = dict(h=30, w=54, frames=10, n_obj=5)                       # BASELINE.json configs[1]
+LONGV = dict(h=30, w=54, frames=9, n_obj=1, n_long=10_000)          # BASELINE.json configs[2]: long-term memory engaged
 BATCH = int(os.environ.get('VOSMEM_BENCH_BATCH', 11))                                                         # sequences per GPU of --workload davis_batch (configs[4]): 11 x 13 query tiles = 143 CTAs
 LVOS = dict(h=68, w=120, n_long=100_000, work_frames=0, n_obj=1)   # BASELINE.json configs[3]
 METRIC = 'memory_readout_query_frames_per_sec'
@@ -163,6 +164,9 @@ def cpu_reference_rate(workload, seconds_budget=12.0, min_calls=3, max_calls=40)
     if workload in ('davis5', 'davis_batch'):
         fill_memory(ref, g, DAVIS['h'], DAVIS['w'], DAVIS['frames'], DAVIS['n_obj'], 'cpu')
         h, w = DAVIS['h'], DAVIS['w']
+    elif workload == 'long_video':
+        fill_memory(ref, g, LONGV['h'], LONGV['w'], LONGV['frames'], LONGV['n_obj'], 'cpu', n_long=LONGV['n_long'])
+        h, w = LONGV['h'], LONGV['w']
     else:
         # bounded sample of the LVOS workload: a quarter of the query rows against the full bank
         fill_memory(ref, g, 17, 120, 1, 1, 'cpu', n_long=LVOS['n_long'])
@@ -175,7 +179,7 @@ def cpu_reference_rate(workload, seconds_budget=12.0, min_calls=3, max_calls=40)
         t0 = time.perf_counter()
         ref.match_memory(qk, qe)
         times.append(time.perf_counter() - t0)
-    scale = 1.0 if workload in ('davis5', 'davis_batch') else (17 * 120) / (LVOS['h'] * LVOS['w'])
+    scale = 1.0 if workload != 'lvos_sharded' else (17 * 120) / (LVOS['h'] * LVOS['w'])
     return scale / statistics.median(times), len(times), torch.get_num_threads()
 
 
@@ -200,6 +204,12 @@ def workload_config(workload, n_gpus):
                  launch='one CUDA-graph replay per step; a step = one frame of each of the sequences (vosmem_match_batch)',
                  parallelism=f'dp{n_gpus} x {BATCH} independent sequences per GPU')
         return c
+    if workload == 'long_video':
+        return dict(workload='long_video_longterm_readout', hw=LONGV['h'] * LONGV['w'],
+                    memory_elements=LONGV['n_long'] + LONGV['frames'] * LONGV['h'] * LONGV['w'], long_term_elements=LONGV['n_long'],
+                    objects=1, ck=CK, cv=CV, top_k=TOP_K, value_storage='bf16',
+                    similarity='bf16 hi/lo split x3 -> fp32 (tcgen05)', l2='flushed before every timed step',
+                    launch='one CUDA-graph replay per step', parallelism=f'dp{n_gpus} (one independent sequence per GPU)')
     if workload == 'davis5':
         return dict(workload='davis2017_multiobject_readout', hw=DAVIS['h'] * DAVIS['w'],
                     memory_elements=DAVIS['frames'] * DAVIS['h'] * DAVIS['w'], objects=DAVIS['n_obj'], ck=CK, cv=CV,
@@ -237,16 +247,17 @@ def run_ours(args, rank, world, local_rank):
         engine.load_long_term(k, s, v)
         n_mem = LVOS['n_long']
     else:
-        h, w, n_obj = DAVIS['h'], DAVIS['w'], DAVIS['n_obj']
+        shape = LONGV if args.workload == 'long_video' else DAVIS
+        h, w, n_obj = shape['h'], shape['w'], shape['n_obj']
         n_seq = BATCH if args.workload == 'davis_batch' else 1
         mgrs = []
         for _ in range(n_seq):
             m = vos.MemoryManager(xmem_config(vosmem_value_dtype='bf16'))
-            fill_memory(m, g, h, w, DAVIS['frames'], n_obj, dev)
+            fill_memory(m, g, h, w, shape['frames'], n_obj, dev, n_long=shape.get('n_long', 0))
             m.create_hidden_state(n_obj, torch.empty(1, CK, h, w, device=dev))
             mgrs.append(m)
         mgr = mgrs[0]
-        n_mem = mgr.work_mem.size
+        n_mem = mgr.work_mem.size + (mgr.long_mem.size if mgr.long_mem.engaged() else 0)
     hw = h * w
     rows = n_obj * CV
 
@@ -268,10 +279,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident steps: stage-split so each stage has its own events ---------------------
     if not sharded:
-        work = mgr.work_mem
-        seg = [work.key_segment(0, n_mem)]
-        vals = [work.value_segment(0, 0, with_usage=True)]
-        out = torch.empty((rows, hw), dtype=torch.float32, device=dev)
+        def single_problem(j):
+            """the (single) object group of the sequence as the arguments of one vosmem_match call"""
+            qk, qe = dev_q[j]
+            (p,), _ = mgr._plan_match(qk, qe)
+            return p
 
         from vos_e_sam_b200 import _native as N
 
@@ -282,12 +294,12 @@ def run_ours(args, rank, world, local_rank):
 
         def step(i, ev):
             qk, qe = dev_q[i % pool]
-            q2, e2 = (qk.flatten(2)[0], qe.flatten(2)[0]) if n_seq == 1 else (None, None)
             flush.fill_(i & 0xFF)
             # the C call records ev[0..3] on the stream around its pack / select / readout kernels
             N.lib.vosmem_debug_set_stage_events(ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event, ev[3].cuda_event)
             if n_seq == 1:
-                ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)  # tcgen05 select (packs the query), merge+softmax+readout(+age)
+                p = single_problem(i % pool)
+                ops.match(p.qk, p.qe, p.segments, p.values, p.rows, TOP_K, out=p.out)  # tcgen05 select (packs the query), merge+softmax+readout(+age)
             else:
                 ops.match_batch(batch_problems(i % pool), TOP_K)
             ev[4].record()
@@ -317,9 +329,9 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(side):
             for j in range(pool):
                 if n_seq == 1:
-                    qk, qe = dev_q[j]
-                    q2, e2 = qk.flatten(2)[0], qe.flatten(2)[0]
-                    run = lambda: ops.match(q2, e2, seg, vals, rows, TOP_K, out=out)
+                    p = single_problem(j)
+                    graph_outputs.append(p)
+                    run = lambda: ops.match(p.qk, p.qe, p.segments, p.values, p.rows, TOP_K, out=p.out)
                 else:
                     probs = batch_problems(j)
                     graph_outputs.append(probs)      # the captured kernels write these tensors on every replay
@@ -474,7 +486,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='davis5', choices=['davis5', 'davis_batch', 'lvos_sharded'])
+    ap.add_argument('--workload', default='davis5', choices=['davis5', 'davis_batch', 'long_video', 'lvos_sharded'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

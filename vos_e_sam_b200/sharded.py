@@ -80,7 +80,7 @@ class CudaBackend:
 class ShardedLongTermReadout:
     """Long-term memory bank sharded along N across `world` ranks (BASELINE.json configs[3])."""
 
-    launches_per_match = 5  # pack_query, select, merge_splits, merge_lists, softmax_readout
+    launches_per_match = 4  # select_tc (packs the query), merge_splits, merge_lists, softmax_readout
 
     def __init__(self, config: dict, rank: int, world: int, device, backend=None, group=None):
         self.top_k = config['top_k']
