@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   volatile uint32_t *epi_done = reinterpret_cast<volatile uint32_t *>(smem + SM_TMEM + 4);
   volatile float *tau_sh = reinterpret_cast<volatile float *>(smem + SM_TAU);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are known to be convergent and
+  // the MMA warp's address arithmetic can live in uniform registers
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int qtile = blockIdx.x;
   const int vsplits = a.splits * HALVES;         // virtual splits: rows of pub / the exchange buffers
   const int64_t g_lo = a.tiles_total * blockIdx.y / a.splits;
@@ -392,7 +394,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(FULL, *tmem_slot, 0);   // provably warp-uniform
+  // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation can only start at
+  // column 0, lane 0.  Treating the base as the constant 0 makes every tcgen05 address a compile-time function of
+  // uniform loop counters: the MMA warp then needs no register -> uniform-register moves per instruction and is no
+  // longer bound by its own issue rate.  Anything else is a configuration this kernel was not built for.
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
   if (dbg && threadIdx.x == 0) dbg[21] = clock64() - t_entry;   // prologue
 
   if (warp == W_REFRESH) {
@@ -418,18 +425,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       // stages 0-1 hold the query image until the MMA warp has copied it to tensor memory: key tile i goes to stage
       // (i + 2) % STAGES, so the first key tile streams in meanwhile
       long long t_wait = 0;
+      // both segments' tile streams as plain scalars (the descriptor sits in parameter space behind blockIdx.z)
+      const int64_t tiles0 = a.seg[0].tiles;
+      const unsigned char *src0 = a.seg[0].image + (a.seg[0].tile0 + g_lo) * KEY_TILE_BYTES;
+      const unsigned char *src1 = a.seg[1].image + (a.seg[1].tile0 + g_lo - tiles0) * KEY_TILE_BYTES;
       for (int i = 0; i < n_tiles; ++i) {
         const int st = (i + 2) % STAGES;
         if (i == 1) ptx::mbar_wait_backoff(bar_qdone, 0, 64);
         const long long t0 = clock64();
         ptx::mbar_wait_backoff(bar_empty + st, ((i / STAGES) & 1) ^ 1, 128);
         t_wait += clock64() - t0;
-        const int64_t g = g_lo + i;
-        const int sg = g >= a.seg[0].tiles;
-        const int64_t tile = sg ? a.seg[1].tile0 + (g - a.seg[0].tiles) : a.seg[0].tile0 + g;
+        const unsigned char *src = (g_lo + i >= tiles0 ? src1 : src0) + (int64_t)i * KEY_TILE_BYTES;
         ptx::mbar_arrive_expect_tx(bar_full + st, KEY_TILE_BYTES);
-        ptx::bulk_g2s(smem + SM_K + st * KEY_TILE_BYTES, a.seg[sg].image + tile * KEY_TILE_BYTES, KEY_TILE_BYTES,
-                      bar_full + st);
+        ptx::bulk_g2s(smem + SM_K + st * KEY_TILE_BYTES, src, KEY_TILE_BYTES, bar_full + st);
       }
       if (dbg) dbg[0] = t_wait;
     }
