@@ -125,6 +125,10 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_a, uint32_t k_base, uin
   ptx::umma_bf16_ts_elect(tmem_d, tmem_a + 128, k0 + 16 * STEP, IDESC, 1);
 }
 
+// cycle counter for the optional per-role timing: only read when a timing buffer is attached (the reads and the
+// bookkeeping around them are not free in the MMA issue loop)
+#define TICK() (dbg ? clock64() : 0ll)
+
 struct ListState {
   uint32_t base;   // shared-memory byte address of slot 0 of this thread's list
   uint32_t off;    // next free slot
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
   const int n_tiles = (int)(g_hi - g_lo);
   long long *dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 : nullptr;
-  const long long t_entry = clock64();
+  const long long t_entry = TICK();
   unsigned long long g_entry = 0;
   if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
 
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   // longer bound by its own issue rate.  Anything else is a configuration this kernel was not built for.
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
-  if (dbg && threadIdx.x == 0) dbg[21] = clock64() - t_entry;   // prologue
+  if (dbg && threadIdx.x == 0) dbg[21] = TICK() - t_entry;   // prologue
 
   if (warp == W_REFRESH) {
     // ===== threshold refresher: tau_sh[row] = min over the virtual splits of their published lower bound =====
@@ -432,9 +436,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       for (int i = 0; i < n_tiles; ++i) {
         const int st = (i + 2) % STAGES;
         if (i == 1) ptx::mbar_wait_backoff(bar_qdone, 0, 64);
-        const long long t0 = clock64();
-        ptx::mbar_wait_backoff(bar_empty + st, ((i / STAGES) & 1) ^ 1, 128);
-        t_wait += clock64() - t0;
+        const long long t0 = TICK();
+        ptx::mbar_wait_backoff(bar_empty + st, ((i / STAGES) & 1) ^ 1, 20);
+        t_wait += TICK() - t0;
         const unsigned char *src = (g_lo + i >= tiles0 ? src1 : src0) + (int64_t)i * KEY_TILE_BYTES;
         ptx::mbar_arrive_expect_tx(bar_full + st, KEY_TILE_BYTES);
         ptx::bulk_g2s(smem + SM_K + st * KEY_TILE_BYTES, src, KEY_TILE_BYTES, bar_full + st);
@@ -449,23 +453,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       stage_query_in_tmem(ptx::smem_u32(smem + SM_Q), tmem_a);   // the image was packed before the CTA-wide barrier
       ptx::umma_commit_elect(bar_qdone);   // arrives once the copies have read shared memory
       long long t_acc = 0, t_ld = 0, t_issue = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = TICK();
       for (int i = 0; i < n_tiles; ++i) {
         const int st = (i + 2) % STAGES, buf = i % ACC_BUFS;
-        const long long t0 = clock64();
-        ptx::mbar_wait_backoff(bar_tempty + buf, ((i / ACC_BUFS) & 1) ^ 1, 64);
-        const long long t1 = clock64();
-        ptx::mbar_wait_backoff(bar_full + st, (i / STAGES) & 1, 32);
-        const long long t2 = clock64();
+        const long long t0 = TICK();
+        ptx::mbar_wait_backoff(bar_tempty + buf, ((i / ACC_BUFS) & 1) ^ 1, 20);
+        const long long t1 = TICK();
+        ptx::mbar_wait_backoff(bar_full + st, (i / STAGES) & 1, 20);
+        const long long t2 = TICK();
         t_acc += t1 - t0;
         t_ld += t2 - t1;
         ptx::tc_fence_after();
         issue_tile(tmem_a, ptx::smem_u32(smem + SM_K + st * KEY_TILE_BYTES), tmem_base + buf * TK);
         ptx::umma_commit_elect(bar_empty + st);   // key stage reusable once these MMAs have read it
         ptx::umma_commit_elect(bar_tfull + buf);  // accumulator ready for the epilogue
-        t_issue += clock64() - t2;
+        t_issue += TICK() - t2;
       }
-      if (dbg && lane == 0) { dbg[1] = t_acc; dbg[2] = t_ld; dbg[3] = t_issue; dbg[4] = clock64() - t_begin; }
+      if (dbg && lane == 0) { dbg[1] = t_acc; dbg[2] = t_ld; dbg[3] = t_issue; dbg[4] = TICK() - t_begin; }
     }
   } else {
     // ===== epilogue: warps 0-7; warp w owns TMEM lanes 32*(w%4).. and drains the tiles with i % 2 == w/4 =====
@@ -496,12 +500,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
     const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
               edge3 = (int)(a.tiles_total - 1 - g_lo);
-    const long long t_begin = clock64();
+    const long long t_begin = TICK();
     for (int i = __shfl_sync(FULL, grabbed, 0); i < n_tiles; i = __shfl_sync(FULL, grabbed, 0), ++n_done) {
       const int buf = i % ACC_BUFS;
-      const long long tw0 = clock64();
+      const long long tw0 = TICK();
       ptx::mbar_wait(bar_tfull + buf, (i / ACC_BUFS) & 1);
-      t_wait += clock64() - tw0;
+      t_wait += TICK() - tw0;
       ptx::tc_fence_after();
       uint32_t v[TK];
       {
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         ptx::mbar_arrive(bar_tempty + buf);  // accumulator buffer free again
         grabbed = atomicAdd(tile_ctr, 1);
       }
-      const long long tp1 = clock64();
+      const long long tp1 = TICK();
       t_ld += tp1 - tw0;
       st.tau = fmaxf(st.tau, tau_sh[row]);
 
@@ -578,13 +582,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
           shared = tau_sh[row];
         }
         st.tau = fmaxf(st.tau, shared);
-        t_first = clock64() - t0;
+        t_first = TICK() - t0;
       }
       unsigned mine = 0;
 #pragma unroll
       for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] > st.tau ? 1u : 0u) << g8;
       const unsigned active = __reduce_or_sync(FULL, mine);
-      const long long tp2 = clock64();
+      const long long tp2 = TICK();
       t_max += tp2 - tp1;
 
       const uint32_t li0 = (uint32_t)i * TK;
@@ -612,22 +616,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
           if (len_bound > PRUNE_ABOVE) {
             len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
             if (len_bound > PRUNE_ABOVE) {
-              const long long tr0 = clock64();
+              const long long tr0 = TICK();
               const float pub_before = st.pub;
               st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
               if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, a.epoch);
-              t_relieve += clock64() - tr0;
+              t_relieve += TICK() - tr0;
               ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
             }
           }
         }
       }
-      t_app += clock64() - tp2;
+      t_app += TICK() - tp2;
     }
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warp retire
-    const long long t_loop = clock64() - t_begin;
+    const long long t_loop = TICK() - t_begin;
 
     // ---- hand the surviving candidates to the merge: both sets of a query share one exchange row, set 0 first.
     //      Lanes run over the entries of a row (coalesced 8-byte stores), four rows per step for ILP. ----
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     if (dbg && lane == 0 && half == 0) {
       dbg[5 + quarter * 2] = t_wait;
       dbg[6 + quarter * 2] = t_relieve;
-      if (quarter == 0) { dbg[13] = t_loop; dbg[14] = clock64() - t_begin; }
+      if (quarter == 0) { dbg[13] = t_loop; dbg[14] = TICK() - t_begin; }
       if (quarter == 1) dbg[15] = t_first;
       if (quarter == 0) { dbg[16] = t_ld; dbg[17] = t_max; dbg[18] = t_app; dbg[19] = n_active; dbg[20] = n_relieve; }
     }
@@ -682,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   if (dbg && threadIdx.x == 0) {
     unsigned long long g_exit;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
-    dbg[22] = clock64() - t_entry;   // whole CTA
+    dbg[22] = TICK() - t_entry;   // whole CTA
     dbg[23] = (long long)g_entry;    // ns, global timer: CTA start / end (spread of the starts, tail of the grid)
     dbg[24] = (long long)g_exit;
   }
