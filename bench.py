@@ -218,7 +218,7 @@ def workload_config(workload, n_gpus):
                     parallelism=f'dp{n_gpus} (one independent sequence per GPU)')
     return dict(workload='lvos1080p_longterm_sharded_readout', hw=LVOS['h'] * LVOS['w'], memory_elements=LVOS['n_long'],
                 objects=1, ck=CK, cv=CV, top_k=TOP_K, value_storage='bf16', l2='flushed before every timed step',
-                parallelism=f'long-term bank sharded along N over {n_gpus} GPU(s), NCCL all-gather of candidates')
+                parallelism=f'long-term bank sharded along N over {n_gpus} GPU(s), candidate exchange: see config.exchange')
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,7 +240,7 @@ def run_ours(args, rank, world, local_rank):
     if sharded:
         from vos_e_sam_b200.sharded import ShardedLongTermReadout
         h, w, n_obj = LVOS['h'], LVOS['w'], 1
-        engine = ShardedLongTermReadout(xmem_config(), rank, world, dev)
+        engine = ShardedLongTermReadout(xmem_config(vosmem_exchange=args.exchange), rank, world, dev)
         gl = torch.Generator().manual_seed(1234 + 4)     # same bank on every rank; each keeps its shard
         k, s, _ = synth.keys(gl, LVOS['n_long'])
         v = torch.randn(n_obj, CV, LVOS['n_long'], generator=gl)
@@ -465,7 +465,8 @@ def run_ours(args, rank, world, local_rank):
                           + ('' if not sharded else ', 1/4 of the query rows, rate scaled'))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                 ms_per_step=total_ms / K, higher_is_better=True, scaling='strong' if sharded else 'weak',
-                vs_baseline=None, dtype='bf16', data='synthetic', config=workload_config(args.workload, world),
+                vs_baseline=None, dtype='bf16', data='synthetic',
+                config=dict(workload_config(args.workload, world), **({'exchange': args.exchange} if sharded else {})),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n_seq * 2 * CK * hw * 4, d2h_bytes_per_step=n_seq * rows * hw * 4),
                 gpu_launches=K * launches_per_step, clocks=clocks.summary(), roofline=dominant,
                 roofline_other=other, cpu_baseline=cpu,
@@ -488,6 +489,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='davis5', choices=['davis5', 'davis_batch', 'long_video', 'lvos_sharded'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'peer'],
+                    help='lvos_sharded: candidate exchange by NCCL all-gather or by peer-memory loads inside the merge kernel')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', 0))
@@ -501,7 +504,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
-               '--workload', args.workload] + (['--no-cpu-baseline'] if args.no_cpu_baseline else [])
+               '--workload', args.workload, '--exchange', args.exchange] + (['--no-cpu-baseline'] if args.no_cpu_baseline else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -46,6 +46,7 @@ enum vosmem_path {
 };
 
 #define VOSMEM_MAX_TOPK 32     /* per-query survivors held one per lane of a warp */
+#define VOSMEM_MAX_LISTS 16   /* candidate lists one merge call takes (ranks of a sharded bank) */
 #define VOSMEM_MAX_BATCH 12   /* problems per vosmem_match_batch call */
 #define VOSMEM_KEY_TILE 64     /* keys per packed image tile */
 #define VOSMEM_QUERY_TILE 128  /* queries per packed image tile (= TMEM lanes) */
@@ -124,6 +125,12 @@ int vosmem_select_topk(const vosmem_select_desc *desc, float *out_score, int64_t
  * global top_k per query.  lists are laid out [list][HW][top_k]. */
 int vosmem_merge_topk(const float *scores, const int64_t *indices, int n_lists, int hw, int top_k,
                       float *out_score, int64_t *out_index, vosmem_stream_t stream);
+
+/* The same with one pointer pair per list (host arrays of `n_lists` device pointers, each list HW x top_k).  The lists
+ * may sit in peer-mapped memory of other GPUs: the kernel then loads them over NVLink itself, i.e. the all-gather of
+ * the sharded long-term readout and the merge are one kernel (vos_e_sam_b200/sharded.py, exchange='peer'). */
+int vosmem_merge_topk_ptrs(const float *const *scores, const int64_t *const *indices, int n_lists, int hw, int top_k,
+                           float *out_score, int64_t *out_index, vosmem_stream_t stream);
 
 /* Values of one object group on the candidate axis. */
 typedef struct vosmem_value_segment {

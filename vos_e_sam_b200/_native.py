@@ -54,6 +54,7 @@ SIGNATURES = {
     'vosmem_pack_values': (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, i64, C.c_int, vp]),
     'vosmem_select_topk': (C.c_int, [C.POINTER(SelectDesc), vp, vp, vp]),
     'vosmem_merge_topk': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    'vosmem_merge_topk_ptrs': (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     'vosmem_softmax_readout': (C.c_int, [C.POINTER(ReadoutDesc), vp, vp, vp]),
     'vosmem_match': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), vp, vp, vp]),
     'vosmem_match_batch': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), C.c_int, vp]),

@@ -91,24 +91,38 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(SplitLists L, int hw,
   }
 }
 
-// Merge `n_lists` already-selected lists (e.g. one per rank): lists[l][q][0..top_k)
-__global__ void merge_lists_kernel(const float *__restrict__ scores, const int64_t *__restrict__ indices, int n_lists,
-                                   int hw, int top_k, float *__restrict__ out_score, int64_t *__restrict__ out_index) {
+// Merge `n_lists` already-selected lists (e.g. one per rank), each [HW][top_k] behind its own pointer: the lists may
+// live in different allocations -- in particular in the peer-mapped memory of other GPUs (NVLink loads), which
+// fuses the candidate all-gather of the sharded long-term readout into this kernel.
+struct ListPtrs {
+  const float *score[VOSMEM_MAX_LISTS];
+  const int64_t *index[VOSMEM_MAX_LISTS];
+};
+
+__global__ void merge_lists_kernel(const __grid_constant__ ListPtrs lists, int n_lists, int hw, int top_k,
+                                   float *__restrict__ out_score, int64_t *__restrict__ out_index) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + warp;
   if (q >= hw) return;
+  // every list's entry for this lane first (independent loads: remote lists cost an NVLink round trip each)
+  float s[VOSMEM_MAX_LISTS];
+  int i[VOSMEM_MAX_LISTS];
+  const int64_t at = (int64_t)q * top_k + lane;
+#pragma unroll
+  for (int l = 0; l < VOSMEM_MAX_LISTS; ++l) {
+    s[l] = -INFINITY;
+    i[l] = 0x7fffffff;
+    if (l < n_lists && lane < top_k) {
+      const int64_t gi = __ldcg(lists.index[l] + at);
+      const float sc = __ldcg(lists.score[l] + at);
+      if (gi >= 0) { s[l] = sc; i[l] = (int)gi; }
+    }
+  }
   WarpTop32 top;
   top.init();
-  for (int l = 0; l < n_lists; ++l) {
-    const int64_t row = ((int64_t)l * hw + q) * top_k;
-    float s = -INFINITY;
-    int i = 0x7fffffff;
-    if (lane < top_k) {
-      int64_t gi = indices[row + lane];
-      if (gi >= 0) { s = scores[row + lane]; i = (int)gi; }
-    }
-    top.push(s, i, lane);
-  }
+#pragma unroll
+  for (int l = 0; l < VOSMEM_MAX_LISTS; ++l)
+    if (l < n_lists) top.push(s[l], i[l], lane);
   if (lane < top_k) {
     const bool have = top.i != 0x7fffffff;
     out_score[(int64_t)q * top_k + lane] = have ? top.s : -INFINITY;
@@ -160,14 +174,40 @@ int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int
 
 using namespace vosmem;
 
-extern "C" int vosmem_merge_topk(const float *scores, const int64_t *indices, int n_lists, int hw, int top_k,
-                                 float *out_score, int64_t *out_index, vosmem_stream_t stream) {
-  VOSMEM_CHECK_ARG(scores && indices && out_score && out_index, "vosmem_merge_topk: null pointer");
-  VOSMEM_CHECK_ARG(n_lists >= 1 && hw >= 1, "vosmem_merge_topk: n_lists=%d hw=%d", n_lists, hw);
-  VOSMEM_CHECK_ARG(top_k >= 1 && top_k <= VOSMEM_MAX_TOPK, "vosmem_merge_topk: top_k=%d outside [1, %d]", top_k,
-                   VOSMEM_MAX_TOPK);
-  merge_lists_kernel<<<(hw + 7) / 8, 256, 0, (cudaStream_t)stream>>>(scores, indices, n_lists, hw, top_k, out_score,
-                                                                    out_index);
+static int launch_merge_lists(const ListPtrs &lists, int n_lists, int hw, int top_k, float *out_score, int64_t *out_index,
+                              cudaStream_t st) {
+  VOSMEM_CHECK_ARG(out_score && out_index, "merge_topk: null output");
+  VOSMEM_CHECK_ARG(n_lists >= 1 && n_lists <= VOSMEM_MAX_LISTS && hw >= 1, "merge_topk: n_lists=%d (max %d) hw=%d", n_lists,
+                   VOSMEM_MAX_LISTS, hw);
+  VOSMEM_CHECK_ARG(top_k >= 1 && top_k <= VOSMEM_MAX_TOPK, "merge_topk: top_k=%d outside [1, %d]", top_k, VOSMEM_MAX_TOPK);
+  merge_lists_kernel<<<(hw + 7) / 8, 256, 0, st>>>(lists, n_lists, hw, top_k, out_score, out_index);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
+}
+
+extern "C" int vosmem_merge_topk(const float *scores, const int64_t *indices, int n_lists, int hw, int top_k,
+                                 float *out_score, int64_t *out_index, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(scores && indices, "vosmem_merge_topk: null pointer");
+  VOSMEM_CHECK_ARG(n_lists >= 1 && n_lists <= VOSMEM_MAX_LISTS, "vosmem_merge_topk: n_lists=%d outside [1, %d]", n_lists,
+                   VOSMEM_MAX_LISTS);
+  ListPtrs lists{};
+  for (int l = 0; l < n_lists; ++l) {
+    lists.score[l] = scores + (int64_t)l * hw * top_k;
+    lists.index[l] = indices + (int64_t)l * hw * top_k;
+  }
+  return launch_merge_lists(lists, n_lists, hw, top_k, out_score, out_index, (cudaStream_t)stream);
+}
+
+extern "C" int vosmem_merge_topk_ptrs(const float *const *scores, const int64_t *const *indices, int n_lists, int hw,
+                                      int top_k, float *out_score, int64_t *out_index, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(scores && indices, "vosmem_merge_topk_ptrs: null pointer array");
+  VOSMEM_CHECK_ARG(n_lists >= 1 && n_lists <= VOSMEM_MAX_LISTS, "vosmem_merge_topk_ptrs: n_lists=%d outside [1, %d]", n_lists,
+                   VOSMEM_MAX_LISTS);
+  ListPtrs lists{};
+  for (int l = 0; l < n_lists; ++l) {
+    VOSMEM_CHECK_ARG(scores[l] && indices[l], "vosmem_merge_topk_ptrs: list %d is null", l);
+    lists.score[l] = scores[l];
+    lists.index[l] = indices[l];
+  }
+  return launch_merge_lists(lists, n_lists, hw, top_k, out_score, out_index, (cudaStream_t)stream);
 }

@@ -145,12 +145,17 @@ def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment
 
 
 def select_topk(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment], top_k: int, index_base: int = 0,
-                path: int = N.PATH_AUTO) -> Tuple[Tensor, Tensor]:
-    """Fused similarity + per-query top-k.  Returns (score, index), both HW x top_k, best first."""
+                path: int = N.PATH_AUTO, out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """Fused similarity + per-query top-k.  Returns (score, index), both HW x top_k, best first (written into `out`
+    when given: contiguous fp32 / int64 tensors of that shape, e.g. views of a peer-mapped exchange buffer)."""
     keep: list = []
     d = _select_desc(qk, qe, segments, top_k, index_base, path, keep)
-    score = torch.empty((d.hw, top_k), dtype=torch.float32, device=qk.device)
-    index = torch.empty((d.hw, top_k), dtype=torch.int64, device=qk.device)
+    if out is not None:
+        score, index = _need(out[0], 'out score'), _need(out[1], 'out index', torch.int64)
+        assert score.shape == (d.hw, top_k) and index.shape == (d.hw, top_k) and score.is_contiguous() and index.is_contiguous()
+    else:
+        score = torch.empty((d.hw, top_k), dtype=torch.float32, device=qk.device)
+        index = torch.empty((d.hw, top_k), dtype=torch.int64, device=qk.device)
     check(N.lib.vosmem_select_topk(C.byref(d), score.data_ptr(), index.data_ptr(), _stream()), 'vosmem_select_topk')
     return score, index
 
@@ -165,6 +170,20 @@ def merge_topk(scores: Tensor, indices: Tensor) -> Tuple[Tensor, Tensor]:
     out_i = torch.empty((hw, k), dtype=torch.int64, device=scores.device)
     check(N.lib.vosmem_merge_topk(scores.data_ptr(), indices.data_ptr(), n_lists, hw, k, out_s.data_ptr(),
                                   out_i.data_ptr(), _stream()), 'vosmem_merge_topk')
+    return out_s, out_i
+
+
+def merge_topk_ptrs(score_ptrs: Sequence[int], index_ptrs: Sequence[int], hw: int, top_k: int,
+                    device: torch.device) -> Tuple[Tensor, Tensor]:
+    """merge_topk over lists given as raw device addresses (one HW x top_k fp32 / int64 pair per list), e.g. the
+    peer-mapped exchange buffers of the other ranks: the kernel reads them over NVLink itself."""
+    n = len(score_ptrs)
+    sp = (C.c_void_p * n)(*score_ptrs)
+    ip = (C.c_void_p * n)(*index_ptrs)
+    out_s = torch.empty((hw, top_k), dtype=torch.float32, device=device)
+    out_i = torch.empty((hw, top_k), dtype=torch.int64, device=device)
+    check(N.lib.vosmem_merge_topk_ptrs(sp, ip, n, hw, top_k, out_s.data_ptr(), out_i.data_ptr(), _stream()),
+          'vosmem_merge_topk_ptrs')
     return out_s, out_i
 
 

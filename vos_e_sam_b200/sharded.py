@@ -65,9 +65,12 @@ class CudaBackend:
         self.ops.pack_values(v, 0, n, self.values, 0)
         return n_obj * cv
 
-    def select(self, qk, qe, top_k, index_base):
+    def select(self, qk, qe, top_k, index_base, out=None):
         n = self.keys.size
-        return self.ops.select_topk(qk, qe, [self.keys.key_segment(0, n)], top_k, index_base=index_base)
+        return self.ops.select_topk(qk, qe, [self.keys.key_segment(0, n)], top_k, index_base=index_base, out=out)
+
+    def merge_ptrs(self, score_ptrs, index_ptrs, hw, top_k):
+        return self.ops.merge_topk_ptrs(score_ptrs, index_ptrs, hw, top_k, self.device)
 
     def merge(self, scores, indices):
         return self.ops.merge_topk(scores, indices)
@@ -77,6 +80,38 @@ class CudaBackend:
         return self.ops.softmax_readout(score, index, [seg], rows, out=out)
 
 
+class PeerExchange:
+    """Candidate exchange without a collective: every rank writes its local top-k lists into a symmetric (peer-mapped)
+    buffer, one device-side barrier tells the ranks that all lists are in place, and the merge kernel loads the other
+    ranks' lists over NVLink itself (vosmem_merge_topk_ptrs).  Two slots alternate between frames, so the single barrier
+    per frame also protects the slot that is overwritten two frames later."""
+
+    def __init__(self, hw: int, top_k: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.hw, self.k = hw, top_k
+        self.score_bytes = hw * top_k * 4
+        self.slot_bytes = hw * top_k * 12                      # fp32 scores + int64 global indices
+        self.buf = symm.empty(2 * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_base = [int(p) for p in self.handle.buffer_ptrs]
+        self.frame = 0
+
+    def slot_views(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(score, index) views of this frame's slot in the local buffer: the selection writes straight into them."""
+        b = (self.frame & 1) * self.slot_bytes
+        score = self.buf[b:b + self.score_bytes].view(torch.float32).view(self.hw, self.k)
+        index = self.buf[b + self.score_bytes:b + self.slot_bytes].view(torch.int64).view(self.hw, self.k)
+        return score, index
+
+    def peer_lists(self) -> Tuple[List[int], List[int]]:
+        b = (self.frame & 1) * self.slot_bytes
+        return [p + b for p in self.peer_base], [p + b + self.score_bytes for p in self.peer_base]
+
+    def barrier_and_advance(self):
+        self.handle.barrier(channel=0)
+        self.frame += 1
+
+
 class ShardedLongTermReadout:
     """Long-term memory bank sharded along N across `world` ranks (BASELINE.json configs[3])."""
 
@@ -84,6 +119,11 @@ class ShardedLongTermReadout:
 
     def __init__(self, config: dict, rank: int, world: int, device, backend=None, group=None):
         self.top_k = config['top_k']
+        # 'nccl': one all-gather of the packed candidates; 'peer': symmetric-memory buffers + NVLink loads inside the
+        # merge kernel (CUDA backend only)
+        self.exchange = str(config.get('vosmem_exchange', 'nccl')).lower()
+        assert self.exchange in ('nccl', 'peer')
+        self._peer = None
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.backend = backend if backend is not None else CudaBackend(device)
         self.n_total = 0
@@ -114,23 +154,39 @@ class ShardedLongTermReadout:
         qk = query_key.flatten(start_dim=2)[0]
         qe = selection.flatten(start_dim=2)[0] if selection is not None else None
         k = self.top_k
+        peer = None
+        if self.exchange == 'peer' and self.world > 1 and hasattr(self.backend, 'merge_ptrs'):
+            if self._peer is None or self._peer.hw != hw:
+                self._peer = PeerExchange(hw, k, qk.device, self.group)      # collective: every rank gets here together
+            peer = self._peer
+        out = peer.slot_views() if peer is not None else None
         if self.hi > self.lo:
-            score, index = self.backend.select(qk, qe, k, self.lo)
-        else:  # empty shard: contributes no candidates
+            score, index = self.backend.select(qk, qe, k, self.lo, out) if out is not None else \
+                self.backend.select(qk, qe, k, self.lo)
+        elif out is not None:   # empty shard: contributes no candidates
+            score, index = out[0].fill_(float('-inf')), out[1].fill_(-1)
+        else:
             score = torch.full((hw, k), float('-inf'), dtype=torch.float32, device=qk.device)
             index = torch.full((hw, k), -1, dtype=torch.int64, device=qk.device)
         if events is not None:
             events[0].record()
+        if peer is not None:
+            # ---- exchange fused into the merge: barrier, then the merge kernel reads every rank's list in place ----
+            score_ptrs, index_ptrs = peer.peer_lists()
+            peer.barrier_and_advance()
+            g_score, g_index = self.backend.merge_ptrs(score_ptrs, index_ptrs, hw, k)
+            all_s = None
         # ---- the one exchange step: all-gather of the local top-k candidates (one message: fp32 score bits and
         #      the global index as int32 pairs, HW * k * 8 bytes per rank) ----
-        if self.world == 1:
+        elif self.world == 1:
             all_s, all_i = score.unsqueeze(0), index.unsqueeze(0)
         else:
             packed = torch.stack((score.view(torch.int32), index.to(torch.int32)))     # 2 x HW x k
             gathered = self._all_gather(packed)                                          # world x 2 x HW x k
             all_s = gathered[:, 0].contiguous().view(torch.float32)
             all_i = gathered[:, 1].to(torch.int64)
-        g_score, g_index = self.backend.merge(all_s, all_i)            # identical on every rank
+        if all_s is not None:
+            g_score, g_index = self.backend.merge(all_s, all_i)            # identical on every rank
         if events is not None:
             events[1].record()
         # ---- readout: values are replicated, so every rank reads out all query rows itself.  (Slicing the query
