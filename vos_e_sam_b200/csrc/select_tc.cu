@@ -557,7 +557,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
           m = lo;
         }
       };
-      if (n_done < TRACK_TILES) {   // group maxima feed the tracker during the first tiles, tile maxima after
+      if (R >= 4 && n_done == 0) {   // first tile of this warp, few virtual splits: every score, so that the R-th best is
+                                     // exact and can be published at once (8 group maxima cannot fill R >= 9 slots)
+#pragma unroll
+        for (int j = 0; j < TK; ++j) track(__uint_as_float(v[j]));
+      } else if (n_done < TRACK_TILES) {   // then the group maxima, tile maxima after the first tiles
 #pragma unroll
         for (int g8 = 0; g8 < TK / 8; ++g8) track(gm[g8]);
       } else {
@@ -570,11 +574,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         st.pub = best[R - 1];
         pub_store(pub_mine + lane, st.pub, a.epoch);
       }
-      if (R <= 3 && n_done == 0) {
-        // First tile of this set with many splits: nothing is known yet and every score would be kept.  The tile
-        // sits in registers, so give the other splits a bounded moment to publish their first values (the MMA warp
-        // keeps filling the other accumulator buffers meanwhile) and filter with the shared threshold.  On a
-        // timeout (e.g. a grid of several waves) the lists overflow and get sorted instead.
+      if (n_done == 0) {
+        // First tile of this warp: nothing is known yet and every score would be kept (and the lists cut by sorting
+        // several times before the thresholds bite).  The tile sits in registers, so give the other virtual splits a
+        // bounded moment to publish the exact R-th best of their first tiles (the MMA warp keeps filling the other
+        // accumulator buffers meanwhile) and filter with the shared threshold.  On a timeout (e.g. a grid of
+        // several waves) the lists overflow and get sorted instead.
         const long long t0 = clock64();
         float shared = tau_sh[row];
         while (__any_sync(FULL, shared == -INFINITY) && clock64() - t0 < FIRST_WAIT_CYCLES) {
