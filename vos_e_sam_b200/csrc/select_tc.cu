@@ -3,36 +3,38 @@
 // Replaces get_similarity + torch.topk of the reference (tracker/model/memory_util.py:7-39,46) for one
 // object group: the N x HW similarity matrix only ever exists as 128 x 64 fp32 tiles in tensor memory.
 //
-//   grid  = (query tiles of 128, N-splits)        one CTA per SM (~200 KB shared memory), 11 warps
+//   grid  = (query tiles of 128, N-splits, problems)   one CTA per SM (~229 KB shared memory), 11 warps;
+//           blockIdx.z selects one of up to MAX_BATCH independent problems (vosmem_match_batch)
 //   prologue         : warps 0-7 pack the CTA's 128-query tile ([-e | 2 q e | -sum e q^2] as bf16 hi / lo, the
 //                      shared-memory layout of a K-major no-swizzle UMMA operand) straight from the fp32 query key /
 //                      selection -- no separate packing kernel, no query image in global memory
 //   warp 8  producer : cp.async.bulk (TMA) of the streamed key tiles, mbarrier full/empty ring of STAGES stages
 //   warp 9  MMA      : copies the query operand into tensor memory once (tcgen05.cp), then per key tile
 //                      25 tcgen05.mma (M128 N64 K16, A from TMEM, B from shared memory; bf16 hi/lo split
-//                      -> fp32) into one of ACC_BUFS accumulator buffers, tcgen05.commit -> mbarriers
+//                      -> fp32) into one of ACC_BUFS accumulator buffers, tcgen05.commit -> mbarriers.  The whole
+//                      warp runs the loop convergently with uniform operands (see the kernel body)
 //   warp 10 refresher: keeps the per-query shared threshold (below) fresh in shared memory
-//   warps 0-7 epilogue: two warp sets, each with one warp per TMEM lane quarter; set 0 drains the even key
-//                      tiles, set 1 the odd ones ("virtual splits": each set has its own lists and
-//                      thresholds), so the fixed per-tile latency of one set hides behind the other.
+//   warps 0-7 epilogue: two warps per TMEM lane quarter, each with its own candidate lists and thresholds ("virtual
+//                      splits"); the tiles of a quarter are handed out dynamically to its two warps.
 //                      tcgen05.ld the tile (thread = query row), append every score above the
 //                      thread's threshold to a private shared-memory candidate list with predicated
 //                      stores (no branches).  Groups of 8 columns in which no lane has a survivor are
 //                      skipped with one warp-wide OR.  When a list fills: drop what fell below the
 //                      (risen) threshold, thread-privately; only if that is not enough the warp cuts
 //                      lists to their best 32 with a bitonic network over packed 32-bit keys.
-// Each CTA leaves <= 64 candidates per query in the exchange buffer; merge_splits_kernel finishes.
+// Each CTA leaves <= 120 candidates per query in the exchange buffer; the merge (merge.cuh) finishes.
 //
 // Thresholds.  A query's threshold is only ever a LOWER bound of its true 32nd-best score, so no true
 // top-k (k <= 32) member is dropped:
-//   local : after a cooperative cut, the (truncated) 32nd-best score of this CTA's own candidates;
-//   shared: every thread tracks, in registers, lower bounds of the R best scores of the keys its warp set has seen
-//           (a sorted insertion of the maxima of the 8-column groups during the first tiles, of the tile maximum
-//           afterwards: maxima of disjoint column sets are scores of distinct keys), R = ceil(33 / virtual splits),
-//           and publishes the R-th after every tile; every cooperative cut also publishes the exact R-th best of
-//           the list it sorted.  The minimum over all virtual splits then has at least 33 keys at or above it.
-//           With S splits running concurrently this tracks the quality of a single pass over all keys, which makes
-//           list overflows (and sorting) rare.
+//   local : after a cooperative cut, the (truncated) 32nd-best score of this warp's own candidates;
+//   shared: every thread tracks, in registers, lower bounds of the R best scores of the keys its warp has seen
+//           (a sorted insertion of every score of the first tile when R >= 4, of the maxima of the 8-column groups
+//           during the first tiles, of the tile maximum afterwards: maxima of disjoint column sets are scores of
+//           distinct keys), R = ceil(33 / virtual splits), and publishes the R-th whenever it rises; every
+//           cooperative cut also publishes the exact R-th best of the list it sorted.  The minimum over all virtual
+//           splits then has at least 33 keys at or above it.  Published values carry the launch epoch (PubEntry),
+//           so nothing has to be reset between launches.  With S splits running concurrently this tracks the
+//           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -43,7 +45,7 @@ constexpr int STAGES = 3;
 constexpr int ACC_BUFS = 5;
 constexpr int TMEM_COLS = 512;            // 5 accumulator buffers (320 columns) + the query operand (136 columns)
 constexpr int TMEM_A = ACC_BUFS * TK;     // first column of the query operand: [hi 64 | lo 64 | tail 8]
-constexpr int HALVES = 2;                 // epilogue warp sets = virtual splits per CTA (set s drains tiles i % 2 == s)
+constexpr int HALVES = 2;                 // epilogue warps per TMEM lane quarter = virtual splits (candidate list sets) per CTA
 constexpr int EPI_WARPS = 4 * HALVES;
 constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_REFRESH = EPI_WARPS + 2;
 constexpr int TC_THREADS = (EPI_WARPS + 3) * 32;   // 352
@@ -53,9 +55,9 @@ constexpr int PRUNE_ABOVE = CSLOTS - 8;     // a list this long may overflow dur
 constexpr int SORT_ABOVE = CSLOTS - 16;     // lists still longer than this after the compaction are cut to their best 32
 constexpr uint32_t SS = CS_E * 8;      // byte stride between consecutive slots of one list
 constexpr uint32_t KEY_SLOT_MASK = 63u;           // low bits of a sort key hold the slot id
-constexpr int FIRST_WAIT_CYCLES = 20000;
+constexpr int FIRST_WAIT_CYCLES = 20000;          // bounded wait for the other virtual splits' first publication
 constexpr int RB = 11;                            // published rows the refresher warp reads per batch (DAVIS: 22 rows = 2 batches)
-constexpr int TRACK_TILES = 16;                   // tiles per warp set during which the subsets' best scores are tracked          // bounded wait for the other splits' first publication
+constexpr int TRACK_TILES = 16;                   // tiles per warp whose group maxima (not just the tile maximum) feed the tracker
 
 // shared memory map (bytes)
 constexpr int SM_K = 0;                                 // key stages; the first two also stage the query image once
