@@ -152,6 +152,12 @@ typedef struct vosmem_readout_desc {
   float *out;           /* rows x HW, row pitch out_ld (the reference's n_g x CV x h x w)      */
   int64_t out_ld;
   float *out_weight;    /* optional HW x top_k softmax weights, or NULL                        */
+  /* Optional grouped output rows: row r lands at out[(r / out_group_rows) * out_group_stride +         */
+  /* (r % out_group_rows) * out_ld + q].  With out_group_rows = CV and out_group_stride = (CV + CH) *  */
+  /* HW the readout is written straight into the channels [0, CV) of the decoder's concatenated       */
+  /* num_objects x (CV + CH) x h x w input (the torch.cat of model/modules.py:232-233).  0 = plain.    */
+  int out_group_rows;
+  int64_t out_group_stride;
 } vosmem_readout_desc;
 
 /* softmax over the top_k survivors (max-subtracted; memory_util.py:48-49), usage scatter-add

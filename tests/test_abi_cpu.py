@@ -48,7 +48,7 @@ def test_struct_layouts_match_the_header(native):
     assert ctypes.sizeof(native.Segment) == 48
     assert ctypes.sizeof(native.SelectDesc) == 16 + 16 + 8 + 2 * 48 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(native.ValueSegment) == 48
-    assert ctypes.sizeof(native.ReadoutDesc) == 24 + 2 * 48 + 24
+    assert ctypes.sizeof(native.ReadoutDesc) == 24 + 2 * 48 + 24 + 16
 
 
 def test_host_side_layout_helpers(native):

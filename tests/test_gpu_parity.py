@@ -391,6 +391,34 @@ def test_match_memory_batch_equals_individual_calls(vos):
         torch.testing.assert_close(b.work_mem.life_count, a.work_mem.life_count)
 
 
+def test_readout_into_decoder_input_buffer(vos):
+    """the readout written straight into channels [0, CV) of the decoder's concatenated
+    num_objects x (CV + CH) x h x w input (model/modules.py:232-233) == torch.cat([match_memory, hidden], 2), for a
+    single-group manager and for one with two object groups (batched launch path)."""
+    g = torch.Generator().manual_seed(31)
+    a, _ = build_manager(vos, g, (10, 16), 5, 3, 64, value_dtype='fp32')
+    z = load('lifecycle_groups.npz')
+    cfg = lifecycle_config(z)
+    cfg['vosmem_value_dtype'] = 'fp32'
+    b = vos.MemoryManager(cfg)
+    replay_lifecycle(z, b, device='cuda')            # ends with two object groups
+    assert b.work_mem.num_groups >= 2
+    for m in (a, b):
+        n_obj = sum(m.work_mem.group_rows(gi) for gi in range(m.work_mem.num_groups)) // m.CV
+        h, w = (10, 16) if m is a else (m.H, m.W)
+        m.hidden = torch.randn(1, n_obj, 64, h, w, device='cuda')
+        qk, qe = synth.query(g, h, w)
+        qk, qe = (qk[:, :m.CK].cuda(), qe[:, :m.CK].cuda())
+        plain = m.match_memory(qk, qe)               # (usage counters do not feed back into the readout)
+        fused = m.readout_with_hidden(qk, qe)
+        torch.cuda.synchronize()
+        assert fused.shape == (1, n_obj, m.CV + 64, h, w)
+        torch.testing.assert_close(fused[0, :, :m.CV], plain, rtol=0, atol=0)
+        torch.testing.assert_close(fused[:, :, m.CV:], m.hidden, rtol=0, atol=0)
+    with pytest.raises(RuntimeError, match='contiguous'):
+        a.match_memory_into(qk, qe, torch.empty(2, 64, 10, 16, device='cuda'))
+
+
 def test_sharded_engine_single_rank_vs_oracle(vos):
     """ShardedLongTermReadout with world == 1 (CUDA backend, bf16 value shadow) == unsharded oracle readout."""
     from vos_e_sam_b200.sharded import ShardedLongTermReadout

@@ -39,7 +39,8 @@ class ValueSegment(C.Structure):
 
 class ReadoutDesc(C.Structure):
     _fields_ = [('hw', C.c_int), ('top_k', C.c_int), ('rows', C.c_int), ('value_dtype', C.c_int),
-                ('n_segments', C.c_int), ('seg', ValueSegment * 2), ('out', vp), ('out_ld', i64), ('out_weight', vp)]
+                ('n_segments', C.c_int), ('seg', ValueSegment * 2), ('out', vp), ('out_ld', i64), ('out_weight', vp),
+                ('out_group_rows', C.c_int), ('out_group_stride', i64)]
 
 
 # name -> (restype, argtypes); mirrors include/vosmem.h one to one (tests check the two agree)

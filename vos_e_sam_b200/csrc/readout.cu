@@ -36,6 +36,8 @@ struct ReadoutArgs {
   float *out;
   int64_t out_ld;
   float *out_weight;
+  int out_group_rows;        // 0 = plain rows x HW
+  int64_t out_group_stride;
 };
 
 struct ReadoutBatch {   // kernel parameter: one ReadoutArgs per problem (blockIdx.z)
@@ -204,7 +206,12 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
     for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
       const int c_local = e / RQ, qq = e % RQ;
       const int ch = ch0 + c_local, q = q0 + qq;
-      if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[qq][c_local];
+      if (ch < a.rows && q < a.hw) {
+        const int64_t at = a.out_group_rows ? (int64_t)(ch / a.out_group_rows) * a.out_group_stride +
+                                                  (int64_t)(ch % a.out_group_rows) * a.out_ld
+                                            : (int64_t)ch * a.out_ld;
+        a.out[at + q] = s_out[qq][c_local];
+      }
     }
     __syncthreads();
   }
@@ -258,6 +265,10 @@ int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
   a.out = d->out;
   a.out_ld = d->out_ld;
   a.out_weight = d->out_weight;
+  VOSMEM_CHECK_ARG(d->out_group_rows >= 0 && (d->out_group_rows == 0 || d->rows % d->out_group_rows == 0),
+                   "readout: out_group_rows=%d does not divide rows=%d", d->out_group_rows, d->rows);
+  a.out_group_rows = d->out_group_rows;
+  a.out_group_stride = d->out_group_stride;
   return VOSMEM_OK;
 }
 

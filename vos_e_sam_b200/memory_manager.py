@@ -84,9 +84,10 @@ class MemoryManager:
         return ops.readout_dense(flat, affinity[0]).view(n_obj, cv, -1)
 
     # ------------------------------------------------------------------------------------------------
-    def _plan_match(self, query_key, selection):
+    def _plan_match(self, query_key, selection, out=None):
         """The object groups of one match_memory call as independent problems (ops.MatchProblem) and the output they
-        fill."""
+        fill.  `out`: optional num_objects x C x h x w buffer with C >= CV (e.g. the decoder's concatenated
+        readout + hidden input); the readout then lands in its channels [0, CV)."""
         work = self.work_mem
         num_groups = work.num_groups
         h, w = query_key.shape[-2:]
@@ -105,7 +106,20 @@ class MemoryManager:
         track_long = use_long and self.enable_long_term_usage
 
         rows_total = sum(work.group_rows(gi) for gi in range(num_groups))
-        out = torch.empty((rows_total, hw), dtype=torch.float32, device=qk.device)
+        if out is None:
+            flat = torch.empty((rows_total, hw), dtype=torch.float32, device=qk.device)
+            result = flat.view(rows_total // self.CV, self.CV, h, w)
+            grouped = None
+        else:
+            ops._need(out, 'out')
+            if out.dim() == 5 and out.shape[0] == 1:
+                out = out[0]
+            if out.dim() != 4 or out.shape[0] * self.CV != rows_total or out.shape[1] < self.CV or \
+                    tuple(out.shape[2:]) != (h, w) or not out.is_contiguous():
+                raise RuntimeError(f'match_memory: `out` must be a contiguous num_objects x (>= CV) x h x w buffer, got '
+                                   f'{tuple(out.shape)} for {rows_total // self.CV} objects, CV={self.CV}, {h}x{w}')
+            result = out[:, :self.CV]
+            grouped = out.view(out.shape[0], out.shape[1], hw)[:, :self.CV]      # objects x CV x HW, object pitch C * HW
 
         problems = []
         row0 = 0
@@ -123,15 +137,23 @@ class MemoryManager:
             values.append(work.value_segment(gi, first, with_usage=(gi == 0 and track_work),
                                              usage_offset=n_work - len_w))
             rows = work.group_rows(gi)
-            problems.append(ops.MatchProblem(qk, qe, segments, values, rows, out[row0:row0 + rows]))
+            dst = flat[row0:row0 + rows] if grouped is None else grouped[row0 // self.CV:(row0 + rows) // self.CV]
+            problems.append(ops.MatchProblem(qk, qe, segments, values, rows, dst))
             row0 += rows
         # life_count += 1 on every store whose usage is recorded (kv_memory_store.py:99) happens inside group 0's
         # readout launch (ValueSegment.life_count), so nothing is left to do after the kernels
-        return problems, out.view(rows_total // self.CV, self.CV, h, w)
+        return problems, result
 
     def match_memory(self, query_key, selection):
         """query_key, selection: B x CK x H x W (B == 1)  ->  num_objects x CV x H x W  (memory_manager.py:57-150)."""
-        problems, out = self._plan_match(query_key, selection)
+        return self.match_memory_into(query_key, selection, None)
+
+    def match_memory_into(self, query_key, selection, out):
+        """match_memory with a caller-provided destination (not in the reference): `out` is a contiguous
+        [1 x] num_objects x (CV + CH) x H x W buffer -- the decoder's concatenated input (model/modules.py:232-233) --
+        whose channels [0, CV) receive the readout directly; the returned tensor is that view (``None``: a fresh
+        num_objects x CV x H x W tensor).  See `readout_with_hidden`."""
+        problems, out = self._plan_match(query_key, selection, out)
         hw = out.shape[-2] * out.shape[-1]
         if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != out.device:
             self._scratch = (torch.empty((hw, self.top_k), dtype=torch.float32, device=out.device),
@@ -145,6 +167,18 @@ class MemoryManager:
             ops.match(p.qk, p.qe, p.segments, p.values, p.rows, self.top_k, out=p.out, path=self.path,
                       scratch=self._scratch)
         return out
+
+    def readout_with_hidden(self, query_key, selection):
+        """``torch.cat([match_memory(...).unsqueeze(0), get_hidden()], 2)`` -- what the decoder consumes
+        (inference_core.py:78-81, model/modules.py:232-233) -- without the copy of the readout: the kernel writes
+        channels [0, CV) of the 1 x num_objects x (CV + CH) x H x W result in place, only the hidden state is copied."""
+        hidden = self.hidden
+        n_obj, ch = hidden.shape[1], hidden.shape[2]
+        h, w = query_key.shape[-2:]
+        fused = torch.empty((1, n_obj, self.CV + ch, h, w), dtype=torch.float32, device=hidden.device)
+        fused[:, :, self.CV:] = hidden
+        self.match_memory_into(query_key, selection, fused)
+        return fused
 
     # ------------------------------------------------------------------------------------------------
     def add_memory(self, key, shrinkage, value, objects, selection=None):

@@ -201,8 +201,14 @@ def _readout_desc(hw: int, top_k: int, rows: int, values: Sequence[ValueSegment]
         g.first, g.count = v.first, v.count
         g.use_count = _p(v.use_count)
         g.life_count = _p(v.life_count)
-    assert out.dim() == 2 and out.shape == (rows, hw) and out.stride(1) == 1
-    d.out, d.out_ld = out.data_ptr(), out.stride(0)
+    if out.dim() == 3:     # grouped rows: objects x CV x HW view of a larger (objects x (CV + CH) x HW) buffer
+        assert out.shape[0] * out.shape[1] == rows and out.shape[2] == hw and out.stride(2) == 1
+        d.out, d.out_ld = out.data_ptr(), out.stride(1)
+        d.out_group_rows, d.out_group_stride = out.shape[1], out.stride(0)
+    else:
+        assert out.dim() == 2 and out.shape == (rows, hw) and out.stride(1) == 1
+        d.out, d.out_ld = out.data_ptr(), out.stride(0)
+        d.out_group_rows, d.out_group_stride = 0, 0
     d.out_weight = _p(out_weight)
     return d
 
