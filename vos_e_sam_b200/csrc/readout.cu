@@ -135,7 +135,9 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
 }
 
 // grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
-template <typename T, int VEC, int RQ, bool FUSED>
+// GROUPED: output rows addressed through out_group_rows / out_group_stride (see vosmem_readout_desc); kept out of the
+// plain instantiation, whose write-out loop is measurably faster without the extra address arithmetic.
+template <typename T, int VEC, int RQ, bool FUSED, bool GROUPED>
 __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __grid_constant__ ReadoutBatch batch) {
   const ReadoutArgs &a = batch.p[blockIdx.z];
   constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering one pass of channels
@@ -203,14 +205,26 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
     }
     __syncthreads();
     // --- write rows x HW with HW contiguous: RQ consecutive queries per row segment ---
-    for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
-      const int c_local = e / RQ, qq = e % RQ;
-      const int ch = ch0 + c_local, q = q0 + qq;
-      if (ch < a.rows && q < a.hw) {
-        const int64_t at = a.out_group_rows ? (int64_t)(ch / a.out_group_rows) * a.out_group_stride +
-                                                  (int64_t)(ch % a.out_group_rows) * a.out_ld
-                                            : (int64_t)ch * a.out_ld;
-        a.out[at + q] = s_out[qq][c_local];
+    if (!GROUPED) {
+      for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
+        const int c_local = e / RQ, qq = e % RQ;
+        const int ch = ch0 + c_local, q = q0 + qq;
+        if (ch < a.rows && q < a.hw) a.out[(int64_t)ch * a.out_ld + q] = s_out[qq][c_local];
+      }
+    } else {
+      // a chunk lies inside one group whenever the group size is a multiple of the chunk (e.g. CV = 512): its base
+      // is then computed once; other group sizes divide per element
+      const int ogr = a.out_group_rows;
+      const bool per_element = ogr % RCH != 0;
+      const int64_t chunk_base = (int64_t)(ch0 / ogr) * a.out_group_stride + (int64_t)(ch0 % ogr) * a.out_ld;
+      for (int e = threadIdx.x; e < RCH * RQ; e += RTHREADS) {
+        const int c_local = e / RQ, qq = e % RQ;
+        const int ch = ch0 + c_local, q = q0 + qq;
+        if (ch < a.rows && q < a.hw) {
+          const int64_t at = per_element ? (int64_t)(ch / ogr) * a.out_group_stride + (int64_t)(ch % ogr) * a.out_ld
+                                         : chunk_base + (int64_t)c_local * a.out_ld;
+          a.out[at + q] = s_out[qq][c_local];
+        }
       }
     }
     __syncthreads();
@@ -226,13 +240,23 @@ int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStrea
     rows = b.p[i].rows > rows ? b.p[i].rows : rows;
   }
   dim3 grid((hw + RQ - 1) / RQ, FUSED ? 1 : (rows + RCH - 1) / RCH, n);
+  bool grouped = false;
+  for (int i = 0; i < n; ++i) grouped = grouped || b.p[i].out_group_rows != 0;
+  for (int i = 0; i < n; ++i)
+    VOSMEM_CHECK_ARG(!grouped || b.p[i].out_group_rows != 0, "readout: grouped and plain output rows in one batch");
+#define VOSMEM_LAUNCH_RD(T, VEC)                                                                    \
+  do {                                                                                              \
+    if (grouped) softmax_readout_kernel<T, VEC, RQ, FUSED, true><<<grid, RTHREADS, 0, st>>>(b);     \
+    else softmax_readout_kernel<T, VEC, RQ, FUSED, false><<<grid, RTHREADS, 0, st>>>(b);            \
+  } while (0)
   if (value_dtype == VOSMEM_F32) {
-    if (vec_ok) softmax_readout_kernel<float, 4, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
-    else softmax_readout_kernel<float, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
+    if (vec_ok) VOSMEM_LAUNCH_RD(float, 4);
+    else VOSMEM_LAUNCH_RD(float, 1);
   } else {
-    if (vec_ok) softmax_readout_kernel<__nv_bfloat16, 8, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
-    else softmax_readout_kernel<__nv_bfloat16, 1, RQ, FUSED><<<grid, RTHREADS, 0, st>>>(b);
+    if (vec_ok) VOSMEM_LAUNCH_RD(__nv_bfloat16, 8);
+    else VOSMEM_LAUNCH_RD(__nv_bfloat16, 1);
   }
+#undef VOSMEM_LAUNCH_RD
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
