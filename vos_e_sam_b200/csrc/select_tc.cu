@@ -3,7 +3,7 @@
 // Replaces get_similarity + torch.topk of the reference (tracker/model/memory_util.py:7-39,46) for one
 // object group: the N x HW similarity matrix only ever exists as 128 x 64 fp32 tiles in tensor memory.
 //
-//   grid  = (query tiles of 128, N-splits, problems)   one CTA per SM (~229 KB shared memory), 11 warps;
+//   grid  = (query tiles of 128, N-splits, problems)   one CTA per SM (~229 KB shared memory), 12 warps;
 //           blockIdx.z selects one of up to MAX_BATCH independent problems (vosmem_match_batch)
 //   prologue         : warps 0-7 pack the CTA's 128-query tile ([-e | 2 q e | -sum e q^2] as bf16 hi / lo, the
 //                      shared-memory layout of a K-major no-swizzle UMMA operand) straight from the fp32 query key /
@@ -13,7 +13,7 @@
 //                      25 tcgen05.mma (M128 N64 K16, A from TMEM, B from shared memory; bf16 hi/lo split
 //                      -> fp32) into one of ACC_BUFS accumulator buffers, tcgen05.commit -> mbarriers.  The whole
 //                      warp runs the loop convergently with uniform operands (see the kernel body)
-//   warp 10 refresher: keeps the per-query shared threshold (below) fresh in shared memory
+//   warps 10-11 refreshers: keep the per-query shared thresholds (below) fresh in shared memory
 //   warps 0-7 epilogue: two warps per TMEM lane quarter, each with its own candidate lists and thresholds ("virtual
 //                      splits"); the tiles of a quarter are handed out dynamically to its two warps.
 //                      tcgen05.ld the tile (thread = query row), append every score above the
@@ -48,7 +48,9 @@ constexpr int TMEM_A = ACC_BUFS * TK;     // first column of the query operand: 
 constexpr int HALVES = 2;                 // epilogue warps per TMEM lane quarter = virtual splits (candidate list sets) per CTA
 constexpr int EPI_WARPS = 4 * HALVES;
 constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_REFRESH = EPI_WARPS + 2;
-constexpr int TC_THREADS = (EPI_WARPS + 3) * 32;   // 352
+constexpr int N_REFRESH = 2;                         // refresher warps: each keeps TQ / N_REFRESH rows of tau_sh fresh
+constexpr int RH = TQ / 32 / N_REFRESH;              // rows per lane of a refresher warp
+constexpr int TC_THREADS = (EPI_WARPS + 2 + N_REFRESH) * 32;   // 384
 constexpr int CSLOTS = 60;             // candidate slots per (virtual split, query) in shared memory
 constexpr int CS_E = TQ + 1;           // 8-byte {score, local index} entries per slot row (+1: bank spread)
 constexpr int PRUNE_ABOVE = CSLOTS - 8;     // a list this long may overflow during the next 8 columns: relieve the warp
@@ -56,7 +58,7 @@ constexpr int SORT_ABOVE = CSLOTS - 16;     // lists still longer than this afte
 constexpr uint32_t SS = CS_E * 8;      // byte stride between consecutive slots of one list
 constexpr uint32_t KEY_SLOT_MASK = 63u;           // low bits of a sort key hold the slot id
 constexpr int FIRST_WAIT_CYCLES = 20000;          // bounded wait for the other virtual splits' first publication
-constexpr int RB = 11;                            // published rows the refresher warp reads per batch (DAVIS: 22 rows = 2 batches)
+constexpr int RB = 22;                            // published rows a refresher warp reads per batch (DAVIS: 22 rows = 1 batch)
 constexpr int TRACK_TILES = 16;                   // tiles per warp whose group maxima (not just the tile maximum) feed the tracker
 
 // shared memory map (bytes)
@@ -272,20 +274,20 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
 // all issued before the first use.
 template <int NB>
 __device__ __forceinline__ void refresh_pass(const PubEntry *pub_row, int vsplits, int hw_pad, uint32_t epoch,
-                                             float (&m)[TQ / 32]) {
+                                             float (&m)[RH]) {
   for (int y0 = 0; y0 < vsplits; y0 += NB) {
-    uint2 raw[NB][TQ / 32];
+    uint2 raw[NB][RH];
 #pragma unroll
     for (int y = 0; y < NB; ++y) {
       const int yy = min(y0 + y, vsplits - 1);
 #pragma unroll
-      for (int h = 0; h < TQ / 32; ++h)
+      for (int h = 0; h < RH; ++h)
         raw[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub_row + (int64_t)yy * hw_pad + 32 * h));
     }
 #pragma unroll
     for (int y = 0; y < NB; ++y)
 #pragma unroll
-      for (int h = 0; h < TQ / 32; ++h)
+      for (int h = 0; h < RH; ++h)
         m[h] = fminf(m[h], raw[y][h].y == epoch ? __uint_as_float(raw[y][h].x) : -INFINITY);
   }
 }
@@ -408,21 +410,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   constexpr uint32_t tmem_base = 0u;
   if (dbg && threadIdx.x == 0) dbg[21] = TICK() - t_entry;   // prologue
 
-  if (warp == W_REFRESH) {
-    // ===== threshold refresher: tau_sh[row] = min over the virtual splits of their published lower bound =====
+  if (warp >= W_REFRESH) {
+    // ===== threshold refreshers: tau_sh[row] = min over the virtual splits of their published lower bound; each of the
+    //       N_REFRESH warps owns TQ / N_REFRESH rows, so a pass over 22 virtual splits is one batch of loads =====
     // (a stale value is still a valid lower bound, so no ordering with the epilogue is needed)
-    const PubEntry *pub_row = a.pub + qtile * TQ + lane;
+    const int row0 = (warp - W_REFRESH) * (TQ / N_REFRESH);
+    const PubEntry *pub_row = a.pub + qtile * TQ + row0 + lane;
     for (int it = 0; *epi_done < EPI_WARPS; ++it) {
-      float m[TQ / 32];
+      float m[RH];
 #pragma unroll
-      for (int h = 0; h < TQ / 32; ++h) m[h] = INFINITY;
+      for (int h = 0; h < RH; ++h) m[h] = INFINITY;
       // rows per batch sized to the number of virtual splits (2: one CTA per query tile, e.g. batched sequences;
-      // 4: two splits, LVOS-size query counts; else 11 at a time), so that no pass re-reads rows for nothing
+      // 4: two splits, LVOS-size query counts; else 22 at a time), so that no pass re-reads rows for nothing
       if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, a.epoch, m);
       else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, a.epoch, m);
       else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, a.epoch, m);
 #pragma unroll
-      for (int h = 0; h < TQ / 32; ++h) tau_sh[lane + 32 * h] = m[h];
+      for (int h = 0; h < RH; ++h) tau_sh[row0 + lane + 32 * h] = m[h];
       if (it >= 16) __nanosleep(256);   // thresholds move fastest during the first tiles
     }
   } else if (warp == W_PRODUCER) {
