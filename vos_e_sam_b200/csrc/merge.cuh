@@ -74,15 +74,46 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
       }
       buffered += add;
     };
+    // A cut above the shared threshold first: the lists typically hold 200-300 candidates at or above tau, of which
+    // 32 are wanted; every 32 that reach the sorting network cost a full bitonic pass.  Bisect (on the value axis,
+    // counting with one warp-wide add per step) for a cut T with 32 <= #{score >= T} <= 40 among the entries in
+    // registers.  #{score >= T} >= 32 is kept invariant, so no member of the best 32 is lost.
+    int n_mine = 0;
+    float s_hi = -INFINITY, s_lo = INFINITY;
+#pragma unroll
+    for (int y = 0; y < MB; ++y) {
+      const int cnt = __shfl_sync(FULL, my_cnt, y);
+      const bool ok = y0 + y < L.splits && lane < cnt && c[y].score >= tau && c[y].index != 0x7fffffff;
+      if (!ok) c[y].score = -INFINITY;
+      else { ++n_mine; s_hi = fmaxf(s_hi, c[y].score); s_lo = fminf(s_lo, c[y].score); }
+    }
+    float cut = tau;
+    if (__reduce_add_sync(FULL, n_mine) > 40) {
+      float lo = warp_min(s_lo), hi = warp_max(s_hi);      // #{score >= lo} = all of them >= 32
+      for (int it = 0; it < 16 && lo < hi; ++it) {
+        const float mid = 0.5f * (lo + hi);
+        int n = 0;
+#pragma unroll
+        for (int y = 0; y < MB; ++y) n += c[y].score >= mid ? 1 : 0;
+        n = __reduce_add_sync(FULL, n);
+        if (n >= 32) {
+          lo = mid;
+          if (n <= 40) break;
+        } else {
+          hi = mid;
+        }
+      }
+      cut = fmaxf(cut, lo);
+    }
 #pragma unroll
     for (int y = 0; y < MB; ++y) {
       if (y0 + y >= L.splits) break;
       const int cnt = __shfl_sync(FULL, my_cnt, y);
-      offer(lane < cnt && c[y].score >= tau && c[y].index != 0x7fffffff, c[y].score, c[y].index);
+      offer(c[y].score >= cut && c[y].score != -INFINITY, c[y].score, c[y].index);
       for (int off = 32; off < cnt; off += 32) {   // rare: a list longer than 32 entries
         const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
         const CandEntry c2 = L.cand[row + off + lane];
-        offer(off + lane < cnt && c2.score >= tau && c2.index != 0x7fffffff, c2.score, c2.index);
+        offer(off + lane < cnt && c2.score >= cut && c2.index != 0x7fffffff, c2.score, c2.index);
       }
     }
   }
