@@ -67,11 +67,18 @@ struct Loader<__nv_bfloat16, 8> {
   using Raw = uint4;
   static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
   static __device__ __forceinline__ void fma(const Raw &raw, float w, float (&acc)[8]) {
+    // packed fp32 FMA (fma.rn.f32x2, sm_100): one instruction per bf16 pair; results are the same two fmaf's
     const unsigned u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      acc[2 * i] = fmaf(w, __uint_as_float(u[i] << 16), acc[2 * i]);
-      acc[2 * i + 1] = fmaf(w, __uint_as_float(u[i] & 0xffff0000u), acc[2 * i + 1]);
+      asm("{\n\t.reg .b64 v, ww, a;\n\t"
+          "mov.b64 v, {%2, %3};\n\t"
+          "mov.b64 ww, {%4, %4};\n\t"
+          "mov.b64 a, {%0, %1};\n\t"
+          "fma.rn.f32x2 a, v, ww, a;\n\t"
+          "mov.b64 {%0, %1}, a;\n\t}"
+          : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1])
+          : "f"(__uint_as_float(u[i] << 16)), "f"(__uint_as_float(u[i] & 0xffff0000u)), "f"(w));
     }
   }
 };
