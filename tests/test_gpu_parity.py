@@ -435,6 +435,21 @@ def test_sharded_engine_single_rank_vs_oracle(vos):
     assert out.shape == want.shape and orc.rel_err(out.cpu(), want) < TOL_BF16
 
 
+def test_peer_exchange_equals_nccl_exchange_on_two_gpus(vos):
+    """Sharded long-term readout on 2 ranks: candidate exchange through peer-mapped memory (the merge kernel loads the
+    other rank's lists over NVLink) == exchange by NCCL all-gather, over several frames (both slots of the double
+    buffer reused).  Needs two GPUs; scripts/peer_check.py is the two-rank program."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29577', os.path.join(root, 'scripts', 'peer_check.py')],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('max |nccl - peer|') == 2
+
+
 def test_errors_are_loud(vos):
     g = torch.Generator().manual_seed(3)
     mk, ms, _ = synth.keys(g, 100)
