@@ -45,6 +45,18 @@ struct ReadoutBatch {   // kernel parameter: one ReadoutArgs per problem (blockI
 };
 static_assert(sizeof(ReadoutBatch) <= 3584, "kernel parameter space");
 
+// (a0, a1) += w * (x0, x1) as one packed fp32 FMA (fma.rn.f32x2, sm_100): the same two fmaf results, half the issue slots
+__device__ __forceinline__ void fma2(float &a0, float &a1, float x0, float x1, float w) {
+  asm("{\n\t.reg .b64 v, ww, a;\n\t"
+      "mov.b64 v, {%2, %3};\n\t"
+      "mov.b64 ww, {%4, %4};\n\t"
+      "mov.b64 a, {%0, %1};\n\t"
+      "fma.rn.f32x2 a, v, ww, a;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(x0), "f"(x1), "f"(w));
+}
+
 template <typename T, int VEC>
 struct Loader;
 template <>
@@ -52,8 +64,8 @@ struct Loader<float, 4> {
   using Raw = float4;
   static __device__ __forceinline__ Raw load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
   static __device__ __forceinline__ void fma(const Raw &v, float w, float (&acc)[4]) {
-    acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
-    acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+    fma2(acc[0], acc[1], v.x, v.y, w);
+    fma2(acc[2], acc[3], v.z, v.w, w);
   }
 };
 template <>
@@ -67,19 +79,10 @@ struct Loader<__nv_bfloat16, 8> {
   using Raw = uint4;
   static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint4 *>(p); }
   static __device__ __forceinline__ void fma(const Raw &raw, float w, float (&acc)[8]) {
-    // packed fp32 FMA (fma.rn.f32x2, sm_100): one instruction per bf16 pair; results are the same two fmaf's
     const unsigned u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      asm("{\n\t.reg .b64 v, ww, a;\n\t"
-          "mov.b64 v, {%2, %3};\n\t"
-          "mov.b64 ww, {%4, %4};\n\t"
-          "mov.b64 a, {%0, %1};\n\t"
-          "fma.rn.f32x2 a, v, ww, a;\n\t"
-          "mov.b64 {%0, %1}, a;\n\t}"
-          : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1])
-          : "f"(__uint_as_float(u[i] << 16)), "f"(__uint_as_float(u[i] & 0xffff0000u)), "f"(w));
-    }
+    for (int i = 0; i < 4; ++i)
+      fma2(acc[2 * i], acc[2 * i + 1], __uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u), w);
   }
 };
 template <>
