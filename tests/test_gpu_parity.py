@@ -340,6 +340,54 @@ def test_match_memory_long_term_multi_object_vs_oracle(vos):
     torch.testing.assert_close(m.long_mem.life_count.cpu(), ref.long_mem.life_count)
 
 
+def test_long_video_shape_vs_oracle(vos):
+    """cfg-3 (BASELINE.json configs[2]) at full size: 10 000 long-term elements + 9 working frames x 1620 tokens, one
+    object, long-term usage counted -- readout and both usage counters against the oracle."""
+    g = torch.Generator().manual_seed(1234 + 3)
+    m, ref = build_manager(vos, g, (30, 54), 9, 1, 512, n_long=10_000, value_dtype='bf16')
+    qk, qe = synth.query(g, 30, 54)
+    got = m.match_memory(qk.cuda(), qe.cuda())
+    want = ref.match_memory(qk, qe)
+    assert got.shape == (1, 512, 30, 54)
+    # parity rule: queries whose k / k+1 fp64 gap is below 1e-3 may legitimately pick either candidate
+    mk = torch.cat([ref.long_mem.key, ref.work_mem.key], -1)
+    ms = torch.cat([ref.long_mem.shrinkage, ref.work_mem.shrinkage], -1)
+    decided = orc.topk_gap(oracle_sim64(mk, ms, qk, qe), 30)[0] > GAP
+    assert float(decided.float().mean()) > 0.8
+    assert orc.rel_err(got.cpu().view(512, -1)[:, decided], want.view(512, -1)[:, decided]) < TOL_BF16
+    # an undecided query moves at most one survivor's weight (a few percent of HW's unit mass) between two keys
+    assert orc.rel_err(m.long_mem.use_count.cpu(), ref.long_mem.use_count) < 5e-2
+    assert orc.rel_err(m.work_mem.use_count.cpu(), ref.work_mem.use_count) < 5e-2
+    assert abs(float(m.long_mem.use_count.sum() + m.work_mem.use_count.sum()) - 1620) < 0.2
+    torch.testing.assert_close(m.long_mem.life_count.cpu(), ref.long_mem.life_count)
+
+
+def test_lvos_shape_tc_matches_simt(vos):
+    """cfg-4 shape (BASELINE.json configs[3]) on one GPU: 100 000 keys x 8160 queries.  The N x HW matrix would be
+    3.3 GB, so the check is size-independent: the tcgen05 selection against the exact fp32 SIMT kernel (scores within
+    2e-3, index sets equal wherever the SIMT k / k+1 gap is decided), and every softmax row of the readout sums to 1."""
+    g = torch.Generator().manual_seed(1234 + 4)
+    n, h, w = 100_000, 68, 120
+    mk, ms, _ = synth.keys(g, n)
+    qk, qe = synth.query(g, h, w)
+    store = vos.KeyValueMemoryStore(count_usage=False)
+    store.add(dev(mk), [torch.zeros(1, 8, n, device='cuda')], dev(ms), None, None)
+    seg = [store.key_segment(0, n)]
+    q2, e2 = dev(qk).flatten(2)[0], dev(qe).flatten(2)[0]
+    s_tc, i_tc = vos.ops.select_topk(q2, e2, seg, 30, path=vos.N.PATH_TCGEN05)
+    s_si, i_si = vos.ops.select_topk(q2, e2, seg, 31, path=vos.N.PATH_SIMT)
+    torch.testing.assert_close(s_tc, s_si[:, :30], rtol=0, atol=2e-3)
+    decided = (s_si[:, 29] - s_si[:, 30]) > 2 * GAP
+    same = (torch.sort(i_tc, 1).values == torch.sort(i_si[:, :30], 1).values).all(1)
+    assert float(decided.float().mean()) > 0.5
+    assert not bool((decided & ~same).any()), f'{int((decided & ~same).sum())} decided queries differ'
+    shadow = torch.randn(n, 64, device='cuda').to(torch.bfloat16)
+    vals = [vos.ops.ValueSegment(shadow=shadow, first=0, count=n)]
+    out, wgt = vos.ops.softmax_readout(s_tc, i_tc, vals, 64, want_weight=True)
+    torch.testing.assert_close(wgt.sum(1), torch.ones(h * w, device='cuda'), rtol=1e-5, atol=1e-5)
+    assert bool(torch.isfinite(out).all())
+
+
 def test_full_size_properties(vos):
     """cfg-2 shape (5 objects, 10 frames x 1620 tokens): properties that hold at any size --
     SIMT and tcgen05 paths agree, the softmax weights of every query sum to 1, usage mass == HW,
