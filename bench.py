@@ -240,7 +240,7 @@ def run_ours(args, rank, world, local_rank):
     if sharded:
         from vos_e_sam_b200.sharded import ShardedLongTermReadout
         h, w, n_obj = LVOS['h'], LVOS['w'], 1
-        engine = ShardedLongTermReadout(xmem_config(vosmem_exchange=args.exchange), rank, world, dev)
+        engine = ShardedLongTermReadout(xmem_config(vosmem_exchange=args.exchange, vosmem_shard=args.shard), rank, world, dev)
         gl = torch.Generator().manual_seed(1234 + 4)     # same bank on every rank; each keeps its shard
         k, s, _ = synth.keys(gl, LVOS['n_long'])
         v = torch.randn(n_obj, CV, LVOS['n_long'], generator=gl)
@@ -466,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                 ms_per_step=total_ms / K, higher_is_better=True, scaling='strong' if sharded else 'weak',
                 vs_baseline=None, dtype='bf16', data='synthetic',
-                config=dict(workload_config(args.workload, world), **({'exchange': args.exchange} if sharded else {})),
+                config=dict(workload_config(args.workload, world), **({'exchange': args.exchange, 'shard': args.shard} if sharded else {})),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n_seq * 2 * CK * hw * 4, d2h_bytes_per_step=n_seq * rows * hw * 4),
                 gpu_launches=K * launches_per_step, clocks=clocks.summary(), roofline=dominant,
                 roofline_other=other, cpu_baseline=cpu,
@@ -489,6 +489,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='davis5', choices=['davis5', 'davis_batch', 'long_video', 'lvos_sharded'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='n', choices=['n', 'queries'],
+                    help='lvos_sharded: shard the key axis (north_star) or, as a control, the query rows')
     ap.add_argument('--exchange', default='nccl', choices=['nccl', 'peer'],
                     help='lvos_sharded: candidate exchange by NCCL all-gather or by peer-memory loads inside the merge kernel')
     args = ap.parse_args()
@@ -504,7 +506,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
-               '--workload', args.workload, '--exchange', args.exchange] + (['--no-cpu-baseline'] if args.no_cpu_baseline else [])
+               '--workload', args.workload, '--exchange', args.exchange, '--shard', args.shard] + (['--no-cpu-baseline'] if args.no_cpu_baseline else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

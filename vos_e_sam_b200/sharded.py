@@ -124,6 +124,11 @@ class ShardedLongTermReadout:
         self.exchange = str(config.get('vosmem_exchange', 'nccl')).lower()
         assert self.exchange in ('nccl', 'peer')
         self._peer = None
+        # 'n' (north_star): the key axis is sharded, candidates are exchanged.  'queries' (the control of SURVEY section
+        # 8e): every rank keeps the whole bank and serves HW / world query rows end to end; the only collective is the
+        # all-gather of the rows x HW readout slices.
+        self.shard = str(config.get('vosmem_shard', 'n')).lower()
+        assert self.shard in ('n', 'queries')
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.backend = backend if backend is not None else CudaBackend(device)
         self.n_total = 0
@@ -133,7 +138,7 @@ class ShardedLongTermReadout:
     def load_long_term(self, key, shrinkage, value) -> None:
         """key 1 x CK x N, shrinkage 1 x 1 x N, value n_obj x CV x N: the whole bank; this rank keeps keys [lo, hi)."""
         self.n_total = key.shape[-1]
-        self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+        self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank) if self.shard == 'n' else (0, self.n_total)
         if self.hi > self.lo:
             self.backend.load_keys(key[:, :, self.lo:self.hi], shrinkage[:, :, self.lo:self.hi])
         self.rows = self.backend.load_values(value)
@@ -154,6 +159,8 @@ class ShardedLongTermReadout:
         qk = query_key.flatten(start_dim=2)[0]
         qe = selection.flatten(start_dim=2)[0] if selection is not None else None
         k = self.top_k
+        if self.shard == 'queries':
+            return self._match_query_sharded(qk, qe, hw, events)
         peer = None
         if self.exchange == 'peer' and self.world > 1 and hasattr(self.backend, 'merge_ptrs'):
             if self._peer is None or self._peer.hw != hw:
@@ -197,3 +204,27 @@ class ShardedLongTermReadout:
         if events is not None:
             events[2].record()
         return out
+
+    def _match_query_sharded(self, qk, qe, hw, events):
+        """Query rows [qlo, qhi) of this rank against the whole bank, then one all-gather of the readout slices."""
+        per = -(-hw // self.world)
+        per = -(-per // 16) * 16                                   # slice starts stay 64-byte aligned
+        qlo, qhi = min(hw, self.rank * per), min(hw, (self.rank + 1) * per)
+        part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
+        if qhi > qlo:
+            sl_k = qk[:, qlo:qhi].contiguous()
+            sl_e = qe[:, qlo:qhi].contiguous() if qe is not None else None
+            score, index = self.backend.select(sl_k, sl_e, self.top_k, 0)
+            if events is not None:
+                events[0].record()
+                events[1].record()
+            self.backend.readout(score, index, self.rows, self.n_total, out=part[:, :qhi - qlo])
+        elif events is not None:
+            events[0].record()
+            events[1].record()
+        if events is not None:
+            events[2].record()
+        if self.world == 1:
+            return part[:, :hw]
+        gathered = self._all_gather(part)                               # world x rows x per
+        return gathered.permute(1, 0, 2).reshape(self.rows, self.world * per)[:, :hw]
