@@ -651,9 +651,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       st.tau = fmaxf(st.tau, tau_sh[row]);
       st = compact_list(st);
       const int my_n = (int)((st.off - st.base) / SS);
-      if (half == 0) n_set0[row] = my_n;
-      // the two warps of a lane quarter meet here (named barrier 1 + quarter, 64 threads)
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      // only the second warp of a lane quarter depends on the first (its entries follow the first one's in the
+      // exchange row): the first arrives on the named barrier 1 + quarter without waiting, the second waits for it
+      if (half == 0) {
+        n_set0[row] = my_n;
+        asm volatile("bar.arrive %0, 64;" ::"r"(1 + quarter) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      }
       const int my_first = half == 0 ? 0 : n_set0[row];
       const int q = qtile * TQ + row;
       if (half == 1 && q < a.hw) a.cand_count[(int64_t)blockIdx.y * a.hw_pad + q] = my_first + my_n;
