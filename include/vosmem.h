@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VOSMEM_ABI_VERSION 1
+#define VOSMEM_ABI_VERSION 2
 
 typedef void *vosmem_stream_t; /* cudaStream_t */
 
@@ -64,6 +64,15 @@ const char *vosmem_status_string(int status);
 int64_t vosmem_key_image_bytes(int ck, int64_t capacity);
 /* scratch bytes vosmem_select_topk / vosmem_match need for `hw` queries over `n_keys` keys */
 int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys);
+/* Zero the control words at the head of a freshly allocated workspace (launch epoch, CTA departure counter, error
+ * flags).  Call ONCE per allocation, before the first select / match call that uses it.  Afterwards the library
+ * maintains the contents: calls that share a workspace must be ordered on one stream (or otherwise serialised), and a
+ * captured CUDA graph of such calls may be replayed with new query / memory contents -- the launch epoch that
+ * validates the published thresholds lives in the workspace and advances on the device with every launch. */
+int vosmem_workspace_init(void *workspace, int64_t workspace_bytes, vosmem_stream_t stream);
+/* Sticky device-side error flags of a workspace; synchronises `stream`.  VOSMEM_OK, or VOSMEM_ENOTSUP when a tcgen05
+ * launch found tensor memory shared with another kernel (its results are then undefined).  Not for the per-frame path. */
+int vosmem_workspace_status(const void *workspace, vosmem_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Store-side packing.  Replaces the torch.cat growth of KeyValueMemoryStore.add
@@ -110,8 +119,8 @@ typedef struct vosmem_select_desc {
   vosmem_segment seg[VOSMEM_MAX_SEGMENTS];
   int64_t index_base;
   int path;                     /* enum vosmem_path                                            */
-  void *workspace;        /* device scratch of >= vosmem_workspace_bytes(): contents need not be initialised nor
-                           * preserved between calls (published thresholds carry a per-launch epoch)        */
+  void *workspace;        /* device scratch of >= vosmem_workspace_bytes(), prepared once by
+                           * vosmem_workspace_init(); not shared by concurrent calls                       */
   int64_t workspace_bytes;
 } vosmem_select_desc;
 

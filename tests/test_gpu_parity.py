@@ -415,6 +415,141 @@ def test_full_size_properties(vos):
     torch.testing.assert_close(r.view(2560, 1620), out, rtol=1e-5, atol=1e-5)
 
 
+def test_davis5_full_size_vs_oracle(vos):
+    """cfg-2, the BENCHMARKED configuration (BASELINE.json configs[1]: 5 objects, 10 frames x 1620 tokens, bf16 value
+    shadow) at full size against the oracle: readout of the decided queries, readout of the undecided ones recomputed
+    in fp64 from the candidates the device picked, and the usage counters."""
+    g = torch.Generator().manual_seed(1234 + 2)
+    m, ref = build_manager(vos, g, (30, 54), 10, 5, 512, value_dtype='bf16')
+    qk, qe = synth.query(g, 30, 54)
+    got = m.match_memory(qk.cuda(), qe.cuda()).cpu().view(2560, 1620)
+    want = ref.match_memory(qk, qe).view(2560, 1620)
+    sim64 = oracle_sim64(ref.work_mem.key, ref.work_mem.shrinkage, qk, qe)
+    decided = orc.topk_gap(sim64, 30)[0] > GAP
+    assert float(decided.float().mean()) > 0.8
+    assert orc.rel_err(got[:, decided], want[:, decided]) < TOL_BF16
+    _, idx = vos.ops.select_topk(qk.cuda().flatten(2)[0], qe.cuda().flatten(2)[0],
+                                 [m.work_mem.key_segment(0, m.work_mem.size)], 30)
+    und = (~decided).nonzero().flatten()
+    redo = readout_from_indices(sim64[:, :, und], ref.work_mem.values[0].reshape(2560, -1), idx.cpu()[und])
+    assert orc.rel_err(got[:, und], redo) < TOL_BF16
+    assert orc.rel_err(m.work_mem.use_count.cpu(), ref.work_mem.use_count) < 1e-2
+    assert abs(float(m.work_mem.use_count.sum()) - 1620) < 0.2
+
+
+def test_lvos_shape_readout_sampled_columns_vs_fp64(vos):
+    """cfg-4 shape (100 000 keys x 8160 queries) through vosmem_match: 512 sampled query columns of the readout
+    against an fp64 evaluation of memory_util.py:7-65 + the value product on those columns (the full N x HW
+    matrix would be 3.3 GB; a column of it is independent of the others)."""
+    g = torch.Generator().manual_seed(1234 + 4)
+    n, h, w, rows = 100_000, 68, 120, 64
+    mk, ms, _ = synth.keys(g, n)
+    qk, qe = synth.query(g, h, w)
+    val = torch.randn(1, rows, n, generator=g)
+    store = vos.KeyValueMemoryStore(count_usage=False, value_dtype=torch.float32)
+    store.add(dev(mk), [dev(val)], dev(ms), None, None)
+    out = vos.ops.match(dev(qk).flatten(2)[0], dev(qe).flatten(2)[0], [store.key_segment(0, n)],
+                        [store.value_segment(0, 0, with_usage=False)], rows, 30).cpu()
+    cols = torch.randperm(h * w, generator=g)[:512]
+    sim64 = oracle_sim64(mk, ms, qk.flatten(2)[:, :, cols], qe.flatten(2)[:, :, cols])        # 1 x N x 512
+    decided = orc.topk_gap(sim64, 30)[0] > GAP
+    assert float(decided.float().mean()) > 0.8
+    want = torch.matmul(val[0].double(), orc.topk_affinity(sim64, 30)[0])                     # rows x 512
+    got = out[:, cols]
+    assert orc.rel_err(got[:, decided], want[:, decided].float()) < TOL_F32
+
+
+@pytest.mark.parametrize('path', ['simt', 'tcgen05'])
+def test_exact_ties_duplicated_frames(vos, path):
+    """Exactly duplicated memory frames (identical keys, shrinkage and values): every score occurs six times.  The
+    reference's torch.topk always returns k candidates; here too -- k distinct valid indices per query, the top-k SCORE
+    multiset of the oracle, and (duplicates carry identical values, so the result is unique) the oracle's readout."""
+    g = torch.Generator().manual_seed(17)
+    h, w, frames, rows = 12, 25, 6, 32
+    hw = h * w
+    k1, s1, _ = synth.keys(g, hw)
+    v1 = torch.randn(1, rows, hw, generator=g)
+    mk, ms, val = k1.repeat(1, 1, frames), s1.repeat(1, 1, frames), v1.repeat(1, 1, frames)
+    n = frames * hw
+    qk, qe = synth.query(g, h, w)
+    store = vos.KeyValueMemoryStore(count_usage=False, value_dtype=torch.float32)
+    store.add(dev(mk), [dev(val)], dev(ms), None, None)
+    p = {'simt': vos.N.PATH_SIMT, 'tcgen05': vos.N.PATH_TCGEN05}[path]
+    q2, e2 = dev(qk).flatten(2)[0], dev(qe).flatten(2)[0]
+    score, index = vos.ops.select_topk(q2, e2, [store.key_segment(0, n)], 30, path=p)
+    index, score = index.cpu(), score.cpu()
+    assert bool((index >= 0).all()) and bool((index < n).all())
+    assert all(len(set(r.tolist())) == 30 for r in index), 'fewer than top_k distinct survivors'
+    sim64 = oracle_sim64(mk, ms, qk, qe)
+    want_scores = torch.topk(sim64[0], 30, dim=0).values.t()                                  # HW x 30, descending
+    assert float((score.double() - want_scores).abs().max()) < 2e-3
+    out = vos.ops.match(q2, e2, [store.key_segment(0, n)], [store.value_segment(0, 0, with_usage=False)], rows, 30,
+                        path=p).cpu()
+    # the k-th / (k+1)-th scores tie exactly for most queries, so "decided" is about distinct VALUES: compare against
+    # the fp64 readout, which is unique because tied keys have identical values
+    want = torch.matmul(val[0].double(), orc.topk_affinity(sim64, 30)[0])
+    gap = orc.topk_gap(sim64, 30)[0]
+    ok = (gap > GAP) | (gap == 0)
+    assert orc.rel_err(out[:, ok], want[:, ok].float()) < 1e-3
+
+
+@pytest.mark.parametrize('path', ['simt', 'tcgen05'])
+def test_exact_ties_all_equal_bank(vos, path):
+    """An all-equal key bank (uniform / black frames): every key scores the same for a query.  k distinct valid
+    survivors, uniform softmax weights, and the readout equals the mean of the chosen value rows."""
+    g = torch.Generator().manual_seed(19)
+    n, h, w, rows = 2000, 9, 16, 16
+    k1, s1, _ = synth.keys(g, 1)
+    mk, ms = k1.repeat(1, 1, n), s1.repeat(1, 1, n)
+    val = torch.randn(1, rows, n, generator=g)
+    qk, qe = synth.query(g, h, w)
+    store = vos.KeyValueMemoryStore(count_usage=False, value_dtype=torch.float32)
+    store.add(dev(mk), [dev(val)], dev(ms), None, None)
+    p = {'simt': vos.N.PATH_SIMT, 'tcgen05': vos.N.PATH_TCGEN05}[path]
+    q2, e2 = dev(qk).flatten(2)[0], dev(qe).flatten(2)[0]
+    score, index = vos.ops.select_topk(q2, e2, [store.key_segment(0, n)], 30, path=p)
+    vals = [store.value_segment(0, 0, with_usage=False)]
+    out, wgt = vos.ops.softmax_readout(score, index, vals, rows, want_weight=True)
+    index = index.cpu()
+    assert bool((index >= 0).all()) and bool((index < n).all())
+    assert all(len(set(r.tolist())) == 30 for r in index), 'fewer than top_k distinct survivors'
+    torch.testing.assert_close(wgt.cpu(), torch.full((h * w, 30), 1 / 30.), rtol=1e-3, atol=1e-4)
+    want = val[0][:, index].mean(-1)                                                          # rows x HW
+    assert orc.rel_err(out.cpu(), want) < 1e-3
+
+
+def test_one_captured_graph_replayed_with_new_queries(vos):
+    """the path must be graph-capturable.  ONE captured graph of vosmem_match, replayed with new
+    query contents in the same buffers (and once after the memory grew in place), must equal the oracle every time:
+    the launch epoch that validates published thresholds is a device-side word, not a host value baked into the graph."""
+    g = torch.Generator().manual_seed(1234 + 9)
+    m, ref = build_manager(vos, g, (30, 54), 6, 2, 64, value_dtype='fp32')
+    qk_d = torch.zeros(1, 64, 30, 54, device='cuda')
+    qe_d = torch.zeros(1, 64, 30, 54, device='cuda')
+    queries = [synth.query(g, 30, 54) for _ in range(4)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        qk_d.copy_(queries[0][0]); qe_d.copy_(queries[0][1])
+        (p,), out = m._plan_match(qk_d, qe_d)
+        run = lambda: vos.ops.match(p.qk, p.qe, p.segments, p.values, p.rows, 30, out=p.out)
+        run()                                         # allocates + initialises the workspace outside the capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    sim_keys = (ref.work_mem.key, ref.work_mem.shrinkage)
+    for qk, qe in queries[1:] + queries[:1]:
+        qk_d.copy_(qk); qe_d.copy_(qe)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = ref.match_memory(qk, qe).view(128, 1620)
+        decided = orc.topk_gap(oracle_sim64(*sim_keys, qk, qe), 30)[0] > GAP
+        got = out.cpu().view(128, 1620)
+        assert orc.rel_err(got[:, decided], want[:, decided]) < TOL_F32
+
+
 def test_match_memory_batch_equals_individual_calls(vos):
     """vosmem_match_batch (independent sequences in one selection + one readout launch, BASELINE configs[4]): three
     managers of different memory sizes / object counts -- one of them with long-term memory and two object groups'

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libvosmem.so')
 
 OK = 0
+ABI_VERSION = 2
 F32, BF16 = 0, 1
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 MAX_TOPK = 32
@@ -51,6 +52,8 @@ SIGNATURES = {
     'vosmem_key_image_bytes': (i64, [C.c_int, i64]),
     'vosmem_workspace_bytes': (i64, [C.c_int, C.c_int, i64]),
     'vosmem_query_image_bytes': (i64, [C.c_int, C.c_int]),
+    'vosmem_workspace_init': (C.c_int, [vp, i64, vp]),
+    'vosmem_workspace_status': (C.c_int, [vp, vp]),
     'vosmem_pack_keys': (C.c_int, [vp, i64, vp, C.c_int, i64, i64, vp, i64, vp]),
     'vosmem_pack_values': (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, i64, C.c_int, vp]),
     'vosmem_select_topk': (C.c_int, [C.POINTER(SelectDesc), vp, vp, vp]),
@@ -84,8 +87,8 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.vosmem_abi_version() != 1:
-        raise NativeLibraryMissing(f'{LIB_PATH}: ABI version {lib.vosmem_abi_version()} != 1, rebuild')
+    if lib.vosmem_abi_version() != ABI_VERSION:
+        raise NativeLibraryMissing(f'{LIB_PATH}: ABI version {lib.vosmem_abi_version()} != {ABI_VERSION}, rebuild')
     return lib
 
 

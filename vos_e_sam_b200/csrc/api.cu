@@ -1,6 +1,4 @@
 // extern "C" entry points that tie the kernels into the calls declared in include/vosmem.h.
-#include <atomic>
-#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -10,7 +8,8 @@
 namespace vosmem {
 
 static thread_local char g_error[512] = "";
-static cudaEvent_t g_stage_events[4] = {nullptr, nullptr, nullptr, nullptr};  // begin / after pack / select / merge|readout
+// debug hook state is per host thread (like the error message): begin / after pack / select / merge|readout
+static thread_local cudaEvent_t g_stage_events[4] = {nullptr, nullptr, nullptr, nullptr};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -101,15 +100,34 @@ extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
   return carve_workspace(nullptr, ck, hw).bytes;
 }
 
+// Zero the control words (launch epoch, departure counter, error flags) once after allocation.
+extern "C" int vosmem_workspace_init(void *workspace, int64_t workspace_bytes, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(workspace != nullptr && workspace_bytes >= 256, "vosmem_workspace_init: workspace of %lld bytes",
+                   (long long)workspace_bytes);
+  VOSMEM_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
+  return VOSMEM_OK;
+}
+
+// Sticky device-side error flags of a workspace (synchronises the stream; not for the per-frame path).
+extern "C" int vosmem_workspace_status(const void *workspace, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(workspace != nullptr, "vosmem_workspace_status: null workspace");
+  WsControl host{};
+  VOSMEM_CUDA(cudaMemcpyAsync(&host, workspace, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  VOSMEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (host.error & WS_ERR_TMEM_BASE) {
+    set_error("select(tcgen05): tensor memory allocation did not start at column 0 (another TMEM user shares the SM)");
+    return VOSMEM_ENOTSUP;
+  }
+  return VOSMEM_OK;
+}
+
 // run the selection kernel(s) of `n` problems: leaves the per-split candidate lists in each problem's workspace
 static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub) {
-  static std::atomic<uint32_t> epoch_counter{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count() | 1u};
   int path = 0, splits = MAX_SPLITS;
   for (int b = 0; b < n; ++b) {
     int rc = validate_select(d + b);
     if (rc != VOSMEM_OK) return rc;
     ws[b] = carve_workspace(d[b].workspace, d[b].ck, d[b].hw);
-    ws[b].epoch = epoch_counter.fetch_add(1, std::memory_order_relaxed);   // tags this launch's published thresholds
     int64_t total = 0;
     for (int s = 0; s < d[b].n_segments; ++s) total += d[b].seg[s].end - d[b].seg[s].begin;
     const int p = resolve_path(d[b]);
@@ -124,7 +142,7 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
     splits = sp < splits ? sp : splits;
   }
   n_lists = splits;                                                          // candidate lists left per query
-  n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : splits;   // published threshold rows
+  n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : 0;        // published threshold rows (SIMT: none)
   if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
   int rc;
   if (path != VOSMEM_PATH_TCGEN05) {   // the tcgen05 kernel packs its query tile itself

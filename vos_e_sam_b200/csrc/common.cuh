@@ -141,9 +141,11 @@ struct CandEntry {   // one exchanged candidate: score + index on the candidate 
 static_assert(sizeof(CandEntry) == 8, "exchange entries are read / written as 8-byte words");
 
 // A published threshold (select_tc.cu, "Thresholds") is only meaningful for the launch that wrote it: the entry
-// carries that launch's epoch and reads of any other epoch see -inf.  The workspace therefore needs no reset
-// between calls (and no initialisation: a stale or uninitialised entry matches the 32-bit epoch of the current
-// launch only by a 2^-32 accident).
+// carries that launch's epoch and reads of any other epoch see -inf, so the workspace needs no reset between
+// calls.  The epoch is a DEVICE-side word of the workspace (WsControl): every CTA of the selection kernel reads
+// it at entry, the last CTA to leave advances it, and the consumer (merge / fused readout) validates against
+// "current - 1".  A captured CUDA graph can therefore be replayed any number of times with new query or memory
+// contents: every replay runs under a fresh epoch (a host-drawn epoch would be baked into the graph).
 struct PubEntry {
   float value;
   uint32_t epoch;
@@ -157,10 +159,19 @@ __device__ __forceinline__ void pub_store(PubEntry *p, float value, uint32_t epo
   __stcg(reinterpret_cast<uint2 *>(p), make_uint2(__float_as_uint(value), epoch));
 }
 
+// Control words at the head of a workspace (zeroed once by vosmem_workspace_init).
+struct WsControl {
+  uint32_t epoch;     // tag of the NEXT tcgen05 selection launch on this workspace
+  uint32_t departed;  // CTAs of the running selection launch that have left (reset by the last one)
+  uint32_t error;     // sticky device-side error flags (WS_ERR_*), read back by vosmem_workspace_status
+  uint32_t pad;
+};
+constexpr uint32_t WS_ERR_TMEM_BASE = 1u;   // tensor-memory allocation did not start at column 0
+
 struct Workspace {
+  WsControl *ctl;              // control words (first 256 bytes)
   unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
   PubEntry *pub;               // pub_rows * hw_pad: lower bound published per (virtual split, query) by the current launch
-  uint32_t epoch;              // of the current launch (set by run_selection)
   CandEntry *cand;             // splits * hw_pad * CAND_SLOTS
   int *cand_count;             // splits * hw_pad
   int pub_rows;                // rows of `pub` (= splits_cap * LISTS_PER_SPLIT)
@@ -190,9 +201,9 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
     off += round_up64(bytes, 256);
     return r;
   };
+  w.ctl = reinterpret_cast<WsControl *>(take(sizeof(WsControl)));
   w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
   w.pub = reinterpret_cast<PubEntry *>(take(cap * hw_pad * 8));
-  w.epoch = 0;
   w.pub_rows = (int)cap;
   w.cand = reinterpret_cast<CandEntry *>(take((int64_t)splits_cap(hw) * hw_pad * CAND_SLOTS * 8));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));

@@ -319,7 +319,7 @@ int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int 
     if (rc != VOSMEM_OK) return rc;
     VOSMEM_CHECK_ARG(d[i].value_dtype == d[0].value_dtype, "readout: problems of one batch must share the value storage type");
     vec_all = vec_all && vec_ok;
-    b.p[i].lists = SplitLists{ws[i].cand, ws[i].cand_count, ws[i].pub, n_lists, n_pub, (int)round_up64(d[i].hw, TQ), ws[i].epoch};
+    b.p[i].lists = SplitLists{ws[i].cand, ws[i].cand_count, ws[i].pub, n_lists, n_pub, (int)round_up64(d[i].hw, TQ), ws[i].ctl};
   }
   return launch<4, true>(b, n, d[0].value_dtype, vec_all, st);
 }

@@ -164,7 +164,7 @@ int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int spl
 int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st) {
   int hw_pad = (int)round_up64(hw, TQ);
-  SplitLists L{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, hw_pad, ws.epoch};
+  SplitLists L{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, hw_pad, ws.ctl};
   merge_splits_kernel<<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;

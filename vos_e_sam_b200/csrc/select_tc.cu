@@ -35,6 +35,8 @@
 //           splits then has at least 33 keys at or above it.  Published values carry the launch epoch (PubEntry),
 //           so nothing has to be reset between launches.  With S splits running concurrently this tracks the
 //           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
+#include <cfloat>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -94,7 +96,7 @@ struct TcArgs {
   int hw, hw_pad, splits;
   const float *qk, *qe;   // query key / selection, CK x hw fp32 (qe may be NULL: isotropic)
   PubEntry *pub;          // [virtual splits][hw_pad] published lower bound per (virtual split, query): see "Thresholds"
-  uint32_t epoch;         // tags this launch's published values
+  WsControl *ctl;         // device-side launch epoch (tags this launch's published values), departure counter, error flags
   CandEntry *cand;
   int *cand_count;
   long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
@@ -375,6 +377,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   // the MMA warp's address arithmetic can live in uniform registers
   const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int qtile = blockIdx.x;
+  // launch epoch: a device-side word, so that a replayed CUDA graph runs under a fresh tag every time.  Nobody
+  // writes it before the last CTA of this launch leaves (bottom of the kernel).
+  const uint32_t epoch = *reinterpret_cast<volatile const uint32_t *>(&a.ctl->epoch);
   const int vsplits = a.splits * HALVES;         // virtual splits: rows of pub / the exchange buffers
   const int64_t g_lo = a.tiles_total * blockIdx.y / a.splits;
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
@@ -406,11 +411,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   // column 0, lane 0.  Treating the base as the constant 0 makes every tcgen05 address a compile-time function of
   // uniform loop counters: the MMA warp then needs no register -> uniform-register moves per instruction and is no
   // longer bound by its own issue rate.  Anything else is a configuration this kernel was not built for.
-  if (*tmem_slot != 0u) __trap();
+  // Not a trap (which would take the whole context down): the CTA flags the workspace, skips its work and leaves
+  // through the common exit; vosmem_workspace_status reports it.
+  const bool tmem_ok = __shfl_sync(FULL, *tmem_slot, 0) == 0u;   // (shuffle: provably warp-uniform, like `warp`)
+  if (!tmem_ok && threadIdx.x == 0) atomicOr(&a.ctl->error, WS_ERR_TMEM_BASE);
   constexpr uint32_t tmem_base = 0u;
   if (dbg && threadIdx.x == 0) dbg[21] = TICK() - t_entry;   // prologue
 
-  if (warp >= W_REFRESH) {
+  if (!tmem_ok) {
+    // (no role runs; the candidate counts of this CTA's queries stay whatever they were: the caller sees the error flag)
+  } else if (warp >= W_REFRESH) {
     // ===== threshold refreshers: tau_sh[row] = min over the virtual splits of their published lower bound; each of the
     //       N_REFRESH warps owns TQ / N_REFRESH rows, so a pass over 22 virtual splits is one batch of loads =====
     // (a stale value is still a valid lower bound, so no ordering with the epilogue is needed)
@@ -422,9 +432,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       for (int h = 0; h < RH; ++h) m[h] = INFINITY;
       // rows per batch sized to the number of virtual splits (2: one CTA per query tile, e.g. batched sequences;
       // 4: two splits, LVOS-size query counts; else 22 at a time), so that no pass re-reads rows for nothing
-      if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, a.epoch, m);
-      else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, a.epoch, m);
-      else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, a.epoch, m);
+      if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
+      else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, epoch, m);
+      else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, epoch, m);
 #pragma unroll
       for (int h = 0; h < RH; ++h) tau_sh[row0 + lane + 32 * h] = m[h];
       if (it >= 16) __nanosleep(256);   // thresholds move fastest during the first tiles
@@ -487,7 +497,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     ListState st;
     st.base = ptx::smem_u32(cs) + row * 8;
     st.off = st.base;
-    st.tau = -INFINITY;
+    // Candidates are kept when score >= threshold: the shared threshold is the score of a real key, and with exact
+    // ties at it (duplicated memory frames, uniform regions) a strict compare would drop keys the reference's
+    // torch.topk returns.  The initial threshold is the lowest FINITE float, not -inf, so that masked columns
+    // (-inf) never qualify.
+    st.tau = -FLT_MAX;
     st.pub = -INFINITY;
     float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
 #pragma unroll
@@ -578,7 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       }
       if (best[R - 1] > st.pub) {
         st.pub = best[R - 1];
-        pub_store(pub_mine + lane, st.pub, a.epoch);
+        pub_store(pub_mine + lane, st.pub, epoch);
       }
       if (n_done == 0) {
         // First tile of this warp: nothing is known yet and every score would be kept (and the lists cut by sorting
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       }
       unsigned mine = 0;
 #pragma unroll
-      for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] > st.tau ? 1u : 0u) << g8;
+      for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] >= st.tau ? 1u : 0u) << g8;
       const unsigned active = __reduce_or_sync(FULL, mine);
       const long long tp2 = TICK();
       t_max += tp2 - tp1;
@@ -613,11 +627,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
           slot[0] = st.off;
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
-            slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) > st.tau ? SS : 0u);
+            slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) >= st.tau ? SS : 0u);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int j = g8 * 8 + jj;
-            if (__uint_as_float(v[j]) > st.tau)
+            if (__uint_as_float(v[j]) >= st.tau)
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot[jj]), "r"(v[j]), "r"(li0 + j) : "memory");
           }
           st.off = slot[8];
@@ -630,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
               const long long tr0 = TICK();
               const float pub_before = st.pub;
               st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
-              if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, a.epoch);
+              if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, epoch);
               t_relieve += TICK() - tr0;
               ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
@@ -698,7 +712,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == W_MMA) ptx::tmem_dealloc(*tmem_slot, TMEM_COLS);
+  // departure: the last CTA of this problem's grid advances the epoch for the next launch on this workspace (every
+  // CTA has read it by then, even in a grid of several waves) and resets the counter
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&a.ctl->departed, 1u) == gridDim.x * gridDim.y - 1) {
+      a.ctl->departed = 0u;
+      a.ctl->epoch = epoch + 1u;
+    }
+  }
   if (dbg && threadIdx.x == 0) {
     unsigned long long g_exit;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
@@ -763,7 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_tile_kernel(const unsigned
 
 }  // namespace
 
-long long *g_tc_debug = nullptr;  // set through vosmem_debug_set_timing_buffer
+thread_local long long *g_tc_debug = nullptr;  // set through vosmem_debug_set_timing_buffer (per host thread)
 
 int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, cudaStream_t st) {
   VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "select(tcgen05): batch of %d problems outside [1, %d]", n, MAX_BATCH);
@@ -796,7 +819,7 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
     a.qk = d.query_key;
     a.qe = d.query_selection;
     a.pub = ws.pub;
-    a.epoch = ws.epoch;
+    a.ctl = ws.ctl;
     a.cand = ws.cand;
     a.cand_count = ws.cand_count;
     a.dbg = g_tc_debug;
@@ -805,13 +828,10 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
   dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits, n);
   // R * (virtual splits) >= 33 keys must stand behind a shared threshold
   const int r = (33 + HALVES * splits - 1) / (HALVES * splits);
+  // the shared-memory opt-in is a per-device function attribute: set it on every launch (a host-side table lookup)
 #define VOSMEM_LAUNCH_TC(RR)                                                                                     \
   do {                                                                                                           \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set) {                                                                                             \
-      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
-      attr_set = true;                                                                                           \
-    }                                                                                                            \
+    VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
     select_tc_kernel<RR><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                                 \
   } while (0)
   if (r <= 1) VOSMEM_LAUNCH_TC(1);

@@ -65,18 +65,33 @@ class ValueSegment:
     life_count: Optional[Tensor] = None  # flat fp32; [0, count) += 1 inside the readout launch when given
 
 
-_workspaces: Dict[Tuple[int, int, int, int], Tensor] = {}
+_workspaces: Dict[Tuple[int, int, int, int, int], Tensor] = {}
 
 
 def workspace_for(device: torch.device, ck: int, hw: int, slot: int = 0) -> Tensor:
-    """Cached per-(device, shape) scratch; `slot` gives the problems of one batch distinct workspaces."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), ck, hw, slot)
+    """Cached scratch per (device, CUDA stream, shape); `slot` gives the problems of one batch distinct workspaces.
+
+    A workspace carries state between the selection kernel and its consumer (candidate lists, published thresholds,
+    the device-side launch epoch), so calls that share one must be stream-ordered: the cache is keyed by the current
+    stream, which gives trackers that run on different streams of one device their own scratch."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(device).cuda_stream, ck, hw, slot)
     ws = _workspaces.get(key)
     if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            # the one-time initialisation must not become a graph node: it would reset the launch epoch on every replay
+            raise RuntimeError('vos_e_sam_b200: run the call once on this stream before capturing it into a CUDA graph '
+                               '(its workspace is allocated and initialised on first use)')
         nbytes = N.lib.vosmem_workspace_bytes(ck, hw, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        check(N.lib.vosmem_workspace_init(ws.data_ptr(), nbytes, _stream()), 'vosmem_workspace_init')
         _workspaces[key] = ws
     return ws
+
+
+def workspace_status(ws: Tensor) -> None:
+    """Raise if a tcgen05 launch on `ws` flagged a device-side error (synchronises the current stream)."""
+    check(N.lib.vosmem_workspace_status(ws.data_ptr(), _stream()), 'vosmem_workspace_status')
 
 
 def key_image_bytes(ck: int, capacity: int) -> int:
