@@ -64,8 +64,8 @@ const char *vosmem_status_string(int status);
 int64_t vosmem_key_image_bytes(int ck, int64_t capacity);
 /* scratch bytes vosmem_select_topk / vosmem_match need for `hw` queries over `n_keys` keys */
 int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys);
-/* Zero the control words at the head of a freshly allocated workspace (launch epoch, CTA departure counter, error
- * flags).  Call ONCE per allocation, before the first select / match call that uses it.  Afterwards the library
+/* Prepare a freshly allocated workspace (zero fill; launch epoch, CTA departure counter and error flags at its
+ * head).  Call ONCE per allocation, before the first select / match call that uses it.  Afterwards the library
  * maintains the contents: calls that share a workspace must be ordered on one stream (or otherwise serialised), and a
  * captured CUDA graph of such calls may be replayed with new query / memory contents -- the launch epoch that
  * validates the published thresholds lives in the workspace and advances on the device with every launch. */
@@ -179,6 +179,58 @@ int vosmem_softmax_readout(const vosmem_readout_desc *desc, const float *score, 
 /* select + softmax + readout for one group in one call (what match_memory does per group). */
 int vosmem_match(const vosmem_select_desc *select, const vosmem_readout_desc *readout,
                  float *scratch_score, int64_t *scratch_index, vosmem_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N-sharded long-term bank (BASELINE configs[3]; no reference counterpart: tools/runner.py:32 is single-GPU).
+ * Rank r owns keys [lo_r, hi_r) and HW / world of the query rows.  Per frame:
+ *   vosmem_select_push      fused similarity + LOCAL top-k over the rank's keys, then every query's (score, global
+ *                           index) list is written straight into the exchange buffer of the rank that OWNS that query
+ *                           (peer-mapped memory: st.global over NVLink), followed by one flag per owner;
+ *   vosmem_exchange_readout waits for the flags of all source ranks, merges the `world` lists of each of its own
+ *                           queries, softmax, usage, sparse readout of its query slice;
+ *   vosmem_push_slice / vosmem_wait_flags   optional: replicate the readout slices on every rank.
+ * No collective and no global barrier: ranks only wait for the data they consume.  Exchange entries are 8 bytes
+ * {fp32 score, int32 global key index}, VOSMEM_EXCH_K per (source rank, query).
+ * ------------------------------------------------------------------------------------------- */
+#define VOSMEM_EXCH_K 32       /* entries per (source rank, query) in an exchange buffer (top_k <= 32, padded)  */
+#define VOSMEM_MAX_RANKS 16
+
+typedef struct vosmem_push_desc {
+  int world, rank;
+  int per;                               /* queries owned by each rank: owner(q) = q / per                         */
+  int64_t index_base;                    /* global index of this rank's first key                                  */
+  void *dst[VOSMEM_MAX_RANKS];           /* per owner: [per][VOSMEM_EXCH_K] x 8 B, this rank's lists for the owner's
+                                            queries (a peer-mapped address for owner != rank)                      */
+  uint32_t *flag[VOSMEM_MAX_RANKS];      /* per owner: word set to `seq` (system-scope release) once the lists have
+                                            landed, or NULL                                                        */
+  uint32_t seq;
+  uint32_t *ticket;                      /* zero-initialised device word of this rank (last-CTA detection)         */
+} vosmem_push_desc;
+
+/* select (desc->index_base is ignored: push->index_base is applied) + merge of the split lists + push */
+int vosmem_select_push(const vosmem_select_desc *select, const vosmem_push_desc *push, vosmem_stream_t stream);
+
+typedef struct vosmem_exchange_desc {
+  const void *lists;        /* [n_lists][list_stride entries] exchange entries of this rank's queries (local memory)  */
+  int n_lists;              /* source ranks                                                                           */
+  int64_t list_stride;      /* entries between consecutive source ranks' lists                                        */
+  int64_t first_entry;      /* entry of query 0 of the readout inside a list (0, or q_lo * VOSMEM_EXCH_K when the lists
+                               cover all queries, e.g. after an NCCL all-gather)                                      */
+  const uint32_t *flags;    /* n_lists words; the kernel waits until each equals `seq` (NULL: no wait)                */
+  uint32_t seq;
+  uint32_t *status;         /* device word, set to 1 if the wait timed out (bounded spin), or NULL                    */
+} vosmem_exchange_desc;
+
+/* readout->hw = number of queries of this rank's slice, readout->out = first column of the slice */
+int vosmem_exchange_readout(const vosmem_readout_desc *readout, const vosmem_exchange_desc *exchange,
+                            vosmem_stream_t stream);
+
+/* Copy the rows x cols block at `src` (row pitch src_ld) to dst[i] (row pitch dst_ld) for every i < n_dst -- the
+ * readout slice of this rank into every rank's full readout -- then set flag[i] = seq (system-scope release). */
+int vosmem_push_slice(const float *src, int64_t src_ld, int rows, int cols, float *const *dst, int64_t dst_ld,
+                      uint32_t *const *flag, int n_dst, uint32_t seq, uint32_t *ticket, vosmem_stream_t stream);
+/* Stream-ordered wait until flags[i] == seq for every bit i of `mask` (bounded spin; *status = 1 on timeout). */
+int vosmem_wait_flags(const uint32_t *flags, uint32_t mask, uint32_t seq, uint32_t *status, vosmem_stream_t stream);
 
 /* life_count[0:n] += 1  (kv_memory_store.py:99) */
 int vosmem_age(float *life_count, int64_t n, vosmem_stream_t stream);

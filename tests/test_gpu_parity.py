@@ -619,9 +619,9 @@ def test_sharded_engine_single_rank_vs_oracle(vos):
 
 
 def test_peer_exchange_equals_nccl_exchange_on_two_gpus(vos):
-    """Sharded long-term readout on 2 ranks: candidate exchange through peer-mapped memory (the merge kernel loads the
-    other rank's lists over NVLink) == exchange by NCCL all-gather, over several frames (both slots of the double
-    buffer reused).  Needs two GPUs; scripts/peer_check.py is the two-rank program."""
+    """Sharded long-term readout on 2 ranks: candidate lists pushed into the owner's peer-mapped memory over NVLink (flags,
+    no collective) == exchange by one NCCL all-to-all == the unsharded readout, gathered and as query slices, over
+    several frames (both slots of the double buffers reused).  Needs two GPUs; scripts/peer_check.py is the program."""
     import os, subprocess, sys
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -630,7 +630,7 @@ def test_peer_exchange_equals_nccl_exchange_on_two_gpus(vos):
                         '--master-addr', '127.0.0.1', '--master-port', '29577', os.path.join(root, 'scripts', 'peer_check.py')],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count('max |nccl - peer|') == 2
+    assert r.stdout.count('max |nccl - peer|') == 2 and r.stdout.count('vs unsharded') == 6
 
 
 def test_errors_are_loud(vos):

@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the host-side protocol of the N-sharded long-term readout
-(shard bounds, candidate all-gather, merge, query-sliced readout, output all-gather) with an oracle-backed
+(shard bounds, per-owner candidate lists, all-to-all, merge, query-sliced readout, output all-gather) with an oracle-backed
 compute backend injected in place of the CUDA kernels.  Result must equal the unsharded oracle readout."""
 import os
 import socket
@@ -14,7 +14,9 @@ from tests import synth
 
 
 class OracleBackend:
-    """CPU stand-in for vos_e_sam_b200.sharded.CudaBackend (test infrastructure)."""
+    """CPU stand-in for vos_e_sam_b200.sharded.CudaBackend (test infrastructure): the same calls, on the tensors the
+    engine passes next to the raw addresses (collective exchange mode only -- there is no peer memory on the CPU)."""
+    K = 32     # sharded.EXCH_K
 
     def load_keys(self, key, shrinkage):
         self.key, self.shrinkage = key, shrinkage
@@ -23,25 +25,32 @@ class OracleBackend:
         self.value = value.reshape(-1, value.shape[-1])
         return self.value.shape[0]
 
-    def select(self, qk, qe, top_k, index_base):
-        sim = orc.anisotropic_l2(self.key, self.shrinkage, qk.unsqueeze(0), qe.unsqueeze(0) if qe is not None else None)
-        kk = min(top_k, sim.shape[1])
-        v, i = torch.topk(sim[0], kk, dim=0)                       # kk x HW
-        score = torch.full((sim.shape[2], top_k), float('-inf'))
-        index = torch.full((sim.shape[2], top_k), -1, dtype=torch.int64)
-        score[:, :kk], index[:, :kk] = v.t(), i.t() + index_base
-        return score, index
+    def new_buffer(self, nbytes):
+        return torch.zeros(nbytes, dtype=torch.uint8)
 
-    def merge(self, scores, indices):
-        g, hw, k = scores.shape
-        s = scores.permute(1, 0, 2).reshape(hw, g * k)
-        i = indices.permute(1, 0, 2).reshape(hw, g * k)
-        v, pos = torch.topk(s, k, dim=1)
-        return v, torch.gather(i, 1, pos)
+    def select_push(self, qk, qe, top_k, index_base, per, world, rank, dst_ptrs, flag_ptrs, seq, ticket_ptr, send=None):
+        assert flag_ptrs is None and send is not None
+        hw = qk.shape[1]
+        score = torch.full((world * per, self.K), float('-inf'))
+        index = torch.full((world * per, self.K), -1, dtype=torch.int32)
+        if self.key.shape[-1] > 0:
+            sim = orc.anisotropic_l2(self.key, self.shrinkage, qk.unsqueeze(0), qe.unsqueeze(0) if qe is not None else None)
+            kk = min(top_k, sim.shape[1])
+            v, i = torch.topk(sim[0], kk, dim=0)                       # kk x HW
+            score[:hw, :kk], index[:hw, :kk] = v.t(), (i.t() + index_base).to(torch.int32)
+        packed = torch.stack((score.view(torch.int32), index), dim=-1)           # [world * per][K][2] = 8-byte entries
+        send.view(torch.int32).view(-1)[:packed.numel()].copy_(packed.flatten())
 
-    def readout(self, score, index, rows, n_total, out):
-        w = torch.softmax(score, dim=1)
-        picked = self.value[:, index.clamp(min=0)]                   # rows x hw x k
+    def exchange_readout(self, lists_ptr, n_lists, list_stride, first_entry, flags_ptr, seq, status_ptr, n_q, top_k, rows,
+                         n_total, out, lists=None):
+        assert flags_ptr is None and lists is not None and first_entry == 0
+        e = lists.view(torch.int32).view(-1)[:n_lists * list_stride * 2].view(n_lists, list_stride // self.K, self.K, 2)
+        s = e[..., 0].contiguous().view(torch.float32)[:, :n_q].permute(1, 0, 2).reshape(n_q, -1)
+        i = e[..., 1][:, :n_q].permute(1, 0, 2).reshape(n_q, -1).to(torch.int64)
+        v, pos = torch.topk(s, top_k, dim=1)
+        idx = torch.gather(i, 1, pos)
+        w = torch.softmax(v, dim=1)
+        picked = self.value[:, idx.clamp(min=0)]                       # rows x n_q x k
         out.copy_((picked * w.unsqueeze(0)).sum(-1))
         return out
 
@@ -64,6 +73,9 @@ def _worker(rank, world, port, n, result_path):
     eng = sharded.ShardedLongTermReadout(dict(top_k=30), rank, world, 'cpu', backend=OracleBackend())
     eng.load_long_term(k, s, v)
     out = eng.match(qk, qe)
+    mine = eng.match(qk, qe, gather=False)                     # this rank's query slice only
+    q_lo, q_hi = eng.query_range(45)
+    assert mine.shape == (32, q_hi - q_lo) and torch.equal(mine, out[:, q_lo:q_hi])
     # unsharded oracle
     sim = orc.anisotropic_l2(k, s, qk.flatten(2), qe.flatten(2))
     aff = orc.topk_affinity(sim, 30)
@@ -93,3 +105,4 @@ def test_partition_helpers():
     assert covered == list(range(1000))
     assert sh.shard_bounds(64, 4, 2) == (64, 64)                              # empty shard
     assert sorted(sum((sh.partition_sequences(64, 8, r) for r in range(8)), [])) == list(range(64))
+    assert sh.query_slices(8160, 8) == 1024 and sh.query_slices(1620, 8) == 208 and sh.query_slices(45, 2) == 32

@@ -44,6 +44,20 @@ class ReadoutDesc(C.Structure):
                 ('out_group_rows', C.c_int), ('out_group_stride', i64)]
 
 
+MAX_RANKS = 16
+EXCH_K = 32
+
+
+class PushDesc(C.Structure):
+    _fields_ = [('world', C.c_int), ('rank', C.c_int), ('per', C.c_int), ('index_base', i64), ('dst', vp * MAX_RANKS),
+                ('flag', vp * MAX_RANKS), ('seq', C.c_uint32), ('ticket', vp)]
+
+
+class ExchangeDesc(C.Structure):
+    _fields_ = [('lists', vp), ('n_lists', C.c_int), ('list_stride', i64), ('first_entry', i64), ('flags', vp),
+                ('seq', C.c_uint32), ('status', vp)]
+
+
 # name -> (restype, argtypes); mirrors include/vosmem.h one to one (tests check the two agree)
 SIGNATURES = {
     'vosmem_abi_version': (C.c_int, []),
@@ -63,6 +77,10 @@ SIGNATURES = {
     'vosmem_match': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), vp, vp, vp]),
     'vosmem_match_batch': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(ReadoutDesc), C.c_int, vp]),
     'vosmem_age': (C.c_int, [vp, i64, vp]),
+    'vosmem_select_push': (C.c_int, [C.POINTER(SelectDesc), C.POINTER(PushDesc), vp]),
+    'vosmem_exchange_readout': (C.c_int, [C.POINTER(ReadoutDesc), C.POINTER(ExchangeDesc), vp]),
+    'vosmem_push_slice': (C.c_int, [vp, i64, C.c_int, C.c_int, C.POINTER(vp), i64, C.POINTER(vp), C.c_int, C.c_uint32, vp, vp]),
+    'vosmem_wait_flags': (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp]),
     'vosmem_similarity_dense': (C.c_int, [vp, i64, vp, vp, vp, C.c_int, i64, C.c_int, vp, vp]),
     'vosmem_softmax_dense': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, vp, i64, vp, vp]),
     'vosmem_readout_dense': (C.c_int, [vp, i64, vp, i64, C.c_int, i64, C.c_int, vp, i64, vp]),

@@ -100,11 +100,13 @@ extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
   return carve_workspace(nullptr, ck, hw).bytes;
 }
 
-// Zero the control words (launch epoch, departure counter, error flags) once after allocation.
+// One-time preparation of a workspace: everything zero (published-threshold entries then carry epoch 0, which no
+// launch ever uses), launch epoch 0x01010101, departure counter and error flags 0.
 extern "C" int vosmem_workspace_init(void *workspace, int64_t workspace_bytes, vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(workspace != nullptr && workspace_bytes >= 256, "vosmem_workspace_init: workspace of %lld bytes",
                    (long long)workspace_bytes);
-  VOSMEM_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
+  VOSMEM_CUDA(cudaMemsetAsync(workspace, 0, (size_t)workspace_bytes, (cudaStream_t)stream));
+  VOSMEM_CUDA(cudaMemsetAsync(workspace, 1, sizeof(uint32_t), (cudaStream_t)stream));   // WsControl::epoch
   return VOSMEM_OK;
 }
 
@@ -155,6 +157,13 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
   if (g_stage_events[2]) cudaEventRecord(g_stage_events[2], st);
   return VOSMEM_OK;
 }
+
+namespace vosmem {
+// the selection stage alone, for the sharded path (exchange.cu): candidate lists stay in the workspace
+int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub) {
+  return run_selection(d, 1, st, ws, n_lists, n_pub);
+}
+}  // namespace vosmem
 
 extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score, int64_t *out_index,
                                   vosmem_stream_t stream) {

@@ -143,8 +143,8 @@ static_assert(sizeof(CandEntry) == 8, "exchange entries are read / written as 8-
 // A published threshold (select_tc.cu, "Thresholds") is only meaningful for the launch that wrote it: the entry
 // carries that launch's epoch and reads of any other epoch see -inf, so the workspace needs no reset between
 // calls.  The epoch is a DEVICE-side word of the workspace (WsControl): every CTA of the selection kernel reads
-// it at entry, the last CTA to leave advances it, and the consumer (merge / fused readout) validates against
-// "current - 1".  A captured CUDA graph can therefore be replayed any number of times with new query or memory
+// it at entry, the last CTA to leave advances it (and records the tag it ran under in WsControl::last, which is
+// what the consumer -- merge / fused readout -- validates against).  A captured CUDA graph can therefore be replayed any number of times with new query or memory
 // contents: every replay runs under a fresh epoch (a host-drawn epoch would be baked into the graph).
 struct PubEntry {
   float value;
@@ -161,10 +161,10 @@ __device__ __forceinline__ void pub_store(PubEntry *p, float value, uint32_t epo
 
 // Control words at the head of a workspace (zeroed once by vosmem_workspace_init).
 struct WsControl {
-  uint32_t epoch;     // tag of the NEXT tcgen05 selection launch on this workspace
+  uint32_t epoch;     // tag of the NEXT tcgen05 selection launch on this workspace (first word: see vosmem_workspace_init)
   uint32_t departed;  // CTAs of the running selection launch that have left (reset by the last one)
   uint32_t error;     // sticky device-side error flags (WS_ERR_*), read back by vosmem_workspace_status
-  uint32_t pad;
+  uint32_t last;      // tag the most recent selection launch ran under: what its consumer validates against
 };
 constexpr uint32_t WS_ERR_TMEM_BASE = 1u;   // tensor-memory allocation did not start at column 0
 

@@ -12,8 +12,7 @@ struct SplitLists {
   const int *cand_count;    // [splits][hw_pad]
   const PubEntry *pub;      // [pub_rows][hw_pad] published lower bounds per (virtual split, query) of the selection launch
   int splits, pub_rows, hw_pad;   // pub_rows == 0: the selection published nothing (SIMT path), no threshold
-  const WsControl *ctl;     // the selection launch that filled the lists ran under epoch ctl->epoch - 1 (it advanced the
-                            // word when its last CTA left)
+  const WsControl *ctl;     // ctl->last = the epoch the selection launch that filled the lists ran under
 };
 
 // Folds `buffered` parked candidates into the running best 32.  Out of line and by value: the sorting network is
@@ -60,7 +59,7 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
     }
     if (!tau_ready) {  // lane y owns list y
       if (L.pub_rows > 0) {
-        const uint32_t epoch = __ldcg(&L.ctl->epoch) - 1u;
+        const uint32_t epoch = __ldcg(&L.ctl->last);
         for (int y = lane; y < L.pub_rows; y += 32) tau = fminf(tau, pub_load(L.pub + (int64_t)y * L.hw_pad + q, epoch));
         tau = warp_min(tau);
       } else {

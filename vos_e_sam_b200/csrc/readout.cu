@@ -8,10 +8,12 @@
 // row read.  Bound by L2 -> SM gather bandwidth / latency: algorithmic bytes =
 // rows * min(N, HW*k) * sizeof(value) + rows * HW * 4 (+ the HW*k candidate list).
 //
-// Two front ends share the gather:
-//   staged : score / index lists (HW x k) come from vosmem_select_topk or a cross-rank merge;
-//   fused  : the kernel merges the per-split candidate lists of the selection kernel itself (merge.cuh), one
-//            warp per query, which removes a kernel and a round trip from vosmem_match.
+// Three front ends share the gather:
+//   staged   : score / index lists (HW x k) come from vosmem_select_topk or a cross-rank merge;
+//   fused    : the kernel merges the per-split candidate lists of the selection kernel itself (merge.cuh), one
+//              warp per query, which removes a kernel and a round trip from vosmem_match;
+//   exchange : N-sharded bank -- the kernel waits for the flags of the source ranks, then merges the `world`
+//              exchange lists that the ranks pushed into this rank's memory for its own query slice.
 #include "common.cuh"
 #include "merge.cuh"
 
@@ -21,6 +23,14 @@ namespace {
 
 constexpr int RTHREADS = 256;
 constexpr int RCH = 512;      // value rows (channels) per pass
+constexpr int FRONT_STAGED = 0, FRONT_FUSED = 1, FRONT_EXCHANGE = 2;
+constexpr int EXCH_K = VOSMEM_EXCH_K;
+
+struct ExchEntry {   // one exchanged candidate: score + GLOBAL key index (-1 = none)
+  float score;
+  int index;
+};
+static_assert(sizeof(ExchEntry) == 8, "exchange entries are read / written as 8-byte words");
 
 struct ReadoutArgs {
   const void *shadow[2];
@@ -33,6 +43,12 @@ struct ReadoutArgs {
   const float *score;      // staged front end
   const int64_t *index;
   SplitLists lists;        // fused front end
+  const ExchEntry *exch;   // exchange front end: [n_lists][exch_stride] entries, query q of the slice at exch_first + q * EXCH_K
+  int exch_lists;
+  int64_t exch_stride, exch_first;
+  const uint32_t *exch_flags;
+  uint32_t exch_seq;
+  uint32_t *exch_status;
   float *out;
   int64_t out_ld;
   float *out_weight;
@@ -43,7 +59,7 @@ struct ReadoutArgs {
 struct ReadoutBatch {   // kernel parameter: one ReadoutArgs per problem (blockIdx.z)
   ReadoutArgs p[MAX_BATCH];
 };
-static_assert(sizeof(ReadoutBatch) <= 3584, "kernel parameter space");
+static_assert(sizeof(ReadoutBatch) <= 4000, "kernel parameter space");
 
 // (a0, a1) += w * (x0, x1) as one packed fp32 FMA (fma.rn.f32x2, sm_100): the same two fmaf results, half the issue slots
 __device__ __forceinline__ void fma2(float &a0, float &a1, float x0, float x1, float w) {
@@ -98,14 +114,32 @@ struct Loader<__nv_bfloat16, 1> {
 // survivors without a local row get weight 0 and point at a real row of the query, so the gather needs no branch
 // on validity and never touches uninitialised memory; `any` = the query has at least one local row).
 // Also the usage scatter-add and the optional weight output (only when `side_effects`).
-template <typename T, bool FUSED>
+template <typename T, int FRONT>
 __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool side_effects, float *m_s, int *m_i, int lane,
                                               float *w_out, const T **row_out, int &any) {
   float s = -INFINITY;
   int64_t gi = -1;
   if (q < a.hw) {
-    if (FUSED) {
+    if (FRONT == FRONT_FUSED) {
       const WarpTop32 top = merge_query<12>(a.lists, q, m_s, m_i, lane);
+      if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
+    } else if (FRONT == FRONT_EXCHANGE) {
+      // one entry per lane from every source rank's list, eight lists in flight at a time, folded into the best 32
+      WarpTop32 top;
+      top.init();
+      for (int l0 = 0; l0 < a.exch_lists; l0 += 8) {
+        uint2 raw[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const int ll = min(l0 + l, a.exch_lists - 1);
+          raw[l] = __ldcg(reinterpret_cast<const uint2 *>(a.exch + ll * a.exch_stride + a.exch_first + (int64_t)q * EXCH_K + lane));
+        }
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const bool ok = l0 + l < a.exch_lists && (int)raw[l].y >= 0;
+          top.push(ok ? __uint_as_float(raw[l].x) : -INFINITY, ok ? (int)raw[l].y : 0x7fffffff, lane);
+        }
+      }
       if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
     } else if (lane < a.top_k) {
       s = a.score[(int64_t)q * a.top_k + lane];
@@ -147,8 +181,9 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
 // grid: (ceil(hw / RQ), chunks of RCH rows [1 when FUSED: the CTA walks all chunks]); block RTHREADS.
 // GROUPED: output rows addressed through out_group_rows / out_group_stride (see vosmem_readout_desc); kept out of the
 // plain instantiation, whose write-out loop is measurably faster without the extra address arithmetic.
-template <typename T, int VEC, int RQ, bool FUSED, bool GROUPED>
+template <typename T, int VEC, int RQ, int FRONT, bool GROUPED>
 __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __grid_constant__ ReadoutBatch batch) {
+  constexpr bool FUSED = FRONT == FRONT_FUSED;
   const ReadoutArgs &a = batch.p[blockIdx.z];
   constexpr int TPQ = RCH / VEC >= RTHREADS ? RTHREADS : RCH / VEC;  // threads covering one pass of channels
   constexpr int GROUPS = RTHREADS / TPQ;                             // query groups working concurrently
@@ -173,9 +208,26 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
           a.life_count[sgi][i] += 1.0f;
   }
 
+  // --- exchange front end: wait until every source rank's lists for this rank's queries have landed (bounded spin:
+  //     a rank that never arrives flags the status word instead of hanging the GPU) ---
+  if (FRONT == FRONT_EXCHANGE && a.exch_flags != nullptr) {
+    if (threadIdx.x < a.exch_lists) {
+      const uint32_t *f = a.exch_flags + threadIdx.x;
+      uint32_t v;
+      long long spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == a.exch_seq) break;
+        __nanosleep(100);
+      } while (++spins < (1ll << 24));
+      if (v != a.exch_seq && a.exch_status) *a.exch_status = 1u;
+    }
+    __syncthreads();
+  }
+
   // --- per query (one warp each): survivors -> softmax weights -> value rows ---
   for (int qq = warp; qq < RQ; qq += RTHREADS / 32)
-    resolve_query<T, FUSED>(a, q0 + qq, blockIdx.y == 0, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane, s_w[qq], s_row[qq],
+    resolve_query<T, FRONT>(a, q0 + qq, blockIdx.y == 0, m_s[FUSED ? qq : 0], m_i[FUSED ? qq : 0], lane, s_w[qq], s_row[qq],
                             s_any[qq]);
   __syncthreads();
 
@@ -242,8 +294,9 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
 }
 
 
-template <int RQ, bool FUSED>
+template <int RQ, int FRONT>
 int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStream_t st) {
+  constexpr bool FUSED = FRONT != FRONT_STAGED;   // the CTA walks all row chunks itself (front end done once per query)
   int hw = 0, rows = 0;
   for (int i = 0; i < n; ++i) {
     hw = b.p[i].hw > hw ? b.p[i].hw : hw;
@@ -256,8 +309,8 @@ int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStrea
     VOSMEM_CHECK_ARG(!grouped || b.p[i].out_group_rows != 0, "readout: grouped and plain output rows in one batch");
 #define VOSMEM_LAUNCH_RD(T, VEC)                                                                    \
   do {                                                                                              \
-    if (grouped) softmax_readout_kernel<T, VEC, RQ, FUSED, true><<<grid, RTHREADS, 0, st>>>(b);     \
-    else softmax_readout_kernel<T, VEC, RQ, FUSED, false><<<grid, RTHREADS, 0, st>>>(b);            \
+    if (grouped) softmax_readout_kernel<T, VEC, RQ, FRONT, true><<<grid, RTHREADS, 0, st>>>(b);     \
+    else softmax_readout_kernel<T, VEC, RQ, FRONT, false><<<grid, RTHREADS, 0, st>>>(b);            \
   } while (0)
   if (value_dtype == VOSMEM_F32) {
     if (vec_ok) VOSMEM_LAUNCH_RD(float, 4);
@@ -321,7 +374,7 @@ int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int 
     vec_all = vec_all && vec_ok;
     b.p[i].lists = SplitLists{ws[i].cand, ws[i].cand_count, ws[i].pub, n_lists, n_pub, (int)round_up64(d[i].hw, TQ), ws[i].ctl};
   }
-  return launch<4, true>(b, n, d[0].value_dtype, vec_all, st);
+  return launch<4, FRONT_FUSED>(b, n, d[0].value_dtype, vec_all, st);
 }
 
 }  // namespace vosmem
@@ -338,5 +391,24 @@ extern "C" int vosmem_softmax_readout(const vosmem_readout_desc *d, const float 
   if (rc != VOSMEM_OK) return rc;
   a.score = score;
   a.index = index;
-  return launch<8, false>(b, 1, d->value_dtype, vec_ok, (cudaStream_t)stream);
+  return launch<8, FRONT_STAGED>(b, 1, d->value_dtype, vec_ok, (cudaStream_t)stream);
+}
+
+extern "C" int vosmem_exchange_readout(const vosmem_readout_desc *d, const vosmem_exchange_desc *x, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(x != nullptr && x->lists != nullptr, "vosmem_exchange_readout: null exchange lists");
+  VOSMEM_CHECK_ARG(x->n_lists >= 1 && x->n_lists <= VOSMEM_MAX_RANKS, "vosmem_exchange_readout: n_lists=%d outside [1, %d]",
+                   x->n_lists, VOSMEM_MAX_RANKS);
+  ReadoutBatch b{};
+  ReadoutArgs &a = b.p[0];
+  bool vec_ok;
+  int rc = fill_args(d, a, vec_ok);
+  if (rc != VOSMEM_OK) return rc;
+  a.exch = static_cast<const ExchEntry *>(x->lists);
+  a.exch_lists = x->n_lists;
+  a.exch_stride = x->list_stride;
+  a.exch_first = x->first_entry;
+  a.exch_flags = x->flags;
+  a.exch_seq = x->seq;
+  a.exch_status = x->status;
+  return launch<4, FRONT_EXCHANGE>(b, 1, d->value_dtype, vec_ok, (cudaStream_t)stream);
 }

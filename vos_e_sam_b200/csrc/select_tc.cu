@@ -162,14 +162,6 @@ __device__ __forceinline__ Entry lds_entry(uint32_t addr) {
       : "f"(score), "f"(tau), "r"(index), "n"(CS_E * 8)                                             \
       : "memory")
 
-// Shared threshold of one query: min over the splits of their published r-th best score.
-__device__ __forceinline__ float shared_threshold(const float *pub_q, int splits, int hw_pad) {
-  float m = INFINITY;
-#pragma unroll 4
-  for (int y = 0; y < splits; ++y) m = fminf(m, __ldcg(pub_q + (int64_t)y * hw_pad));
-  return m;
-}
-
 // Called when some list of the warp could overflow during the next 8 columns.  Kept out of line (eight call
 // sites in the unrolled epilogue).  Three steps, cheapest first:
 //   1. pick up the latest shared threshold (warp 6 keeps it fresh in shared memory);
@@ -177,15 +169,18 @@ __device__ __forceinline__ float shared_threshold(const float *pub_q, int splits
 //   3. lists that are still too long are cut to their best 32 by the whole warp, four queries per round
 //      (bitonic network over packed 32-bit keys), which also yields a new local threshold.
 // Every thread drops the entries of its own list that are below its threshold (in place, order kept).
+// The keep test is one float below the append threshold: after a cooperative cut the append threshold is "strictly
+// above the list's 32nd best" (see relieve_lists), and the entries that tie with that 32nd best must stay.
 __device__ __forceinline__ ListState compact_list(ListState st) {
   const int cnt = (int)((st.off - st.base) / SS);
   const int nmax = __reduce_max_sync(FULL, cnt);
+  const float keep = nextafterf(st.tau, -INFINITY);
   uint32_t rd = st.base, wr = st.base;
   for (int e = 0; e < nmax; ++e) {
     const bool in = rd < st.off;
     Entry en = lds_entry(in ? rd : st.base);
     if (!in) en.score = __int_as_float(0x7fc00000);  // NaN never passes the compare
-    VOSMEM_APPEND("ge", wr, en.score, st.tau, en.index);
+    VOSMEM_APPEND("ge", wr, en.score, keep, en.index);
     rd += SS;
   }
   st.off = wr;
@@ -257,11 +252,14 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
     for (int u = 0; u < 4; ++u) {
       if (on[u]) {
         cs[lane * CS_E + row[u]] = sv[u];
-        const float floor32 = ord2f(__shfl_sync(FULL, kc[u], 31) & ~KEY_SLOT_MASK);
+        // This list now holds 32 keys scoring >= their exact minimum, so a later key only matters if it beats that
+        // minimum STRICTLY (a tie is interchangeable with the ones held, as in the reference's torch.topk): without
+        // this, exact ties (duplicated frames, uniform regions) would refill and re-sort the list for ever.
+        const float exact32 = warp_min(sv[u].score);
         const float at_rank = ord2f(__shfl_sync(FULL, kc[u], rank - 1) & ~KEY_SLOT_MASK);   // exact (truncated) rank-th best
         if (lane == src[u]) {
           st.off = st.base + 32 * SS;
-          st.tau = fmaxf(st.tau, floor32);
+          st.tau = fmaxf(st.tau, nextafterf(exact32, INFINITY));
           st.pub = fmaxf(st.pub, at_rank);
         }
       }
@@ -501,7 +499,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // ties at it (duplicated memory frames, uniform regions) a strict compare would drop keys the reference's
     // torch.topk returns.  The initial threshold is the lowest FINITE float, not -inf, so that masked columns
     // (-inf) never qualify.
-    st.tau = -FLT_MAX;
+    // Rows past the last query (the tail of the last query tile) never keep anything: their operand is all zero,
+    // i.e. every key ties at score 0.
+    st.tau = qtile * TQ + row < a.hw ? -FLT_MAX : INFINITY;
     st.pub = -INFINITY;
     float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
 #pragma unroll
@@ -719,7 +719,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     __threadfence();
     if (atomicAdd(&a.ctl->departed, 1u) == gridDim.x * gridDim.y - 1) {
       a.ctl->departed = 0u;
-      a.ctl->epoch = epoch + 1u;
+      a.ctl->last = epoch;
+      a.ctl->epoch = epoch + 1u == 0u ? 1u : epoch + 1u;   // 0 is what never-written entries carry
     }
   }
   if (dbg && threadIdx.x == 0) {

@@ -1,29 +1,43 @@
-"""Multi-GPU readout: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the exchange.
+"""Multi-GPU readout: one process per GPU; NVLink peer memory (or torch.distributed / NCCL) for the exchange.
 
 Two ways the path shards:
 
 1. independent sequences / objects -> plain data parallelism, no collective: every rank runs its own
    ``MemoryManager`` (``partition_sequences`` deals sequences to ranks; used by bench.py --gpus N).
 
-2. one LVOS-scale long-term bank sharded along N (``ShardedLongTermReadout``):
-     rank r owns keys [lo_r, hi_r) (packed image + fp32 keys) -> fused similarity + LOCAL top-k
-     all-gather of the (score, global index) candidates: HW * k * 8 bytes per rank
-     every rank merges the G candidate lists -> the same global top-k (vosmem_merge_topk)
-     softmax + readout on every rank from a replicated value shadow (no second collective and no reduction
-     anywhere: global top-k is a subset of the union of local top-k's, and the softmax needs only the k
-     merged scores).
-   The reference has no counterpart (single GPU, tools/runner.py:32); results equal the unsharded
-   MemoryManager.match_memory by construction, which the tests check.
+2. one LVOS-scale long-term bank sharded along N (``ShardedLongTermReadout``, BASELINE.json configs[3]).  Rank r
+   owns keys [lo_r, hi_r) AND the query rows [q_lo_r, q_hi_r); values are replicated.  Per frame and rank:
 
-The host logic is backend-agnostic so that the protocol is testable with gloo on CPU (tests inject a
-CPU backend built on the oracle); the product backend is ``CudaBackend`` -- kernels of libvosmem.so only.
+     select + push   fused similarity + LOCAL top-k over the rank's keys for all HW queries; the (score, global index)
+                     list of every query goes straight to the rank that OWNS the query.
+                       'peer' : the merge kernel stores into the owner's peer-mapped exchange buffer over NVLink and
+                                raises one flag per owner (system-scope release) -- no collective, no barrier;
+                       'nccl' : the lists are staged locally and exchanged by ONE all-to-all (NCCL; gloo in the CPU
+                                protocol test), HW / world * k * 8 bytes per (source, owner) pair.
+     exchange readout  waits for the source ranks' flags ('peer'), merges the `world` lists of each of its own queries
+                     (global top-k is a subset of the union of local top-k's), softmax, sparse readout of its query
+                     slice from the replicated value shadow.
+     gather (optional)  every rank's slice is replicated on all ranks ('peer': stores into the peers' output buffers +
+                     flags; 'nccl': all-gather).  Callers that consume the slice in place (a decoder sharded the same
+                     way, or a host copy per rank) skip it: ``match(..., gather=False)``.
+
+   Exchanged bytes per rank and frame: HW * k * 8 * (world-1)/world (245 KB per pair at LVOS / 8 ranks) instead of an
+   all-gather's HW * k * 8 per source; the readout is not repeated on every rank.  The reference has no counterpart
+   (single GPU, tools/runner.py:32); results equal the unsharded MemoryManager.match_memory, which the tests check.
+
+The host logic is backend-agnostic so that the protocol is testable with gloo on CPU (tests inject a CPU backend built
+on the oracle); the product backend is ``CudaBackend`` -- kernels of libvosmem.so only.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+import ctypes as C
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+EXCH_K = 32          # entries per (source rank, query) exchange list (vosmem.h: VOSMEM_EXCH_K)
+ENTRY = 8            # bytes per entry: fp32 score + int32 global key index
 
 
 def shard_bounds(n: int, world: int, rank: int, align: int = 64) -> Tuple[int, int]:
@@ -32,6 +46,12 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 64) -> Tuple[int, i
     per = -(-per // align) * align
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+def query_slices(hw: int, world: int, align: int = 16) -> int:
+    """Queries owned by each rank (owner(q) = q // per); slice starts stay 64-byte aligned in fp32 rows."""
+    per = -(-hw // world)
+    return -(-per // align) * align
 
 
 def partition_sequences(n_sequences: int, world: int, rank: int) -> List[int]:
@@ -43,19 +63,19 @@ class CudaBackend:
     """The product backend: every call is a libvosmem.so kernel on the current CUDA stream."""
 
     def __init__(self, device, value_dtype=torch.bfloat16):
-        from . import ops
+        from . import _native, ops
         from .kv_memory_store import KeyValueMemoryStore
-        self.ops, self.device = ops, device
+        self.ops, self.N, self.device = ops, _native, device
         self.store_cls, self.value_dtype = KeyValueMemoryStore, value_dtype
         self.keys = None
         self.values = None
+        self.n_keys = 0
 
     def load_keys(self, key, shrinkage):
         self.keys = self.store_cls(count_usage=False, value_dtype=self.value_dtype)
-        n = key.shape[-1]
         # the key bank carries no values of its own here (values are replicated separately)
         self.keys.add(key.to(self.device), [], shrinkage.to(self.device), None, None)
-        return n
+        self.n_keys = key.shape[-1]
 
     def load_values(self, value):
         """value: n_obj x CV x N (full bank, replicated)."""
@@ -65,68 +85,91 @@ class CudaBackend:
         self.ops.pack_values(v, 0, n, self.values, 0)
         return n_obj * cv
 
-    def select(self, qk, qe, top_k, index_base, out=None):
-        n = self.keys.size
-        return self.ops.select_topk(qk, qe, [self.keys.key_segment(0, n)], top_k, index_base=index_base, out=out)
+    def new_buffer(self, nbytes: int) -> torch.Tensor:
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
 
-    def merge_ptrs(self, score_ptrs, index_ptrs, hw, top_k):
-        return self.ops.merge_topk_ptrs(score_ptrs, index_ptrs, hw, top_k, self.device)
+    def select_push(self, qk, qe, top_k, index_base, per, world, rank, dst_ptrs, flag_ptrs, seq, ticket_ptr, send=None):
+        """Local selection over this rank's keys + push of every query's list to its owner (one C call, two launches).
+        `send`: the tensor behind dst_ptrs in collective mode (unused here: the kernel takes the raw addresses)."""
+        N, ops = self.N, self.ops
+        push = N.PushDesc()
+        push.world, push.rank, push.per, push.index_base = world, rank, per, index_base
+        for r in range(world):
+            push.dst[r] = dst_ptrs[r]
+            push.flag[r] = flag_ptrs[r] if flag_ptrs is not None else None
+        push.seq, push.ticket = seq, ticket_ptr
+        keep: list = []
+        if self.n_keys == 0:
+            raise RuntimeError('CudaBackend.select_push: this rank\'s key shard is empty (use fewer ranks or a larger bank)')
+        seg = [self.keys.key_segment(0, self.n_keys)]
+        sd = ops._select_desc(qk, qe, seg, top_k, 0, N.PATH_AUTO, keep)
+        N.check(N.lib.vosmem_select_push(C.byref(sd), C.byref(push), ops._stream()), 'vosmem_select_push')
 
-    def merge(self, scores, indices):
-        return self.ops.merge_topk(scores, indices)
+    def exchange_readout(self, lists_ptr, n_lists, list_stride, first_entry, flags_ptr, seq, status_ptr, n_q, top_k, rows,
+                         n_total, out, lists=None):
+        """out: rows x n_q view (row pitch = out.stride(0)) of this rank's query slice.  `lists`: the tensor behind
+        lists_ptr in collective mode (unused here)."""
+        N, ops = self.N, self.ops
+        seg = ops.ValueSegment(shadow=self.values, first=0, count=n_total, use_count=None)
+        rd = ops._readout_desc(n_q, top_k, rows, [seg], out, None)
+        x = N.ExchangeDesc()
+        x.lists, x.n_lists, x.list_stride, x.first_entry = lists_ptr, n_lists, list_stride, first_entry
+        x.flags, x.seq, x.status = flags_ptr, seq, status_ptr
+        N.check(N.lib.vosmem_exchange_readout(C.byref(rd), C.byref(x), ops._stream()), 'vosmem_exchange_readout')
+        return out
 
-    def readout(self, score, index, rows, n_total, out):
-        seg = self.ops.ValueSegment(shadow=self.values, first=0, count=n_total, use_count=None)
-        return self.ops.softmax_readout(score, index, [seg], rows, out=out)
+    def push_slice(self, src, dst_ptrs, dst_ld, flag_ptrs, seq, ticket_ptr):
+        N = self.N
+        n = len(dst_ptrs)
+        dp = (C.c_void_p * n)(*dst_ptrs)
+        fp = (C.c_void_p * n)(*flag_ptrs)
+        N.check(N.lib.vosmem_push_slice(src.data_ptr(), src.stride(0), src.shape[0], src.shape[1], dp, dst_ld, fp, n, seq,
+                                        ticket_ptr, self.ops._stream()), 'vosmem_push_slice')
+
+    def wait_flags(self, flags_ptr, mask, seq, status_ptr):
+        self.N.check(self.N.lib.vosmem_wait_flags(flags_ptr, mask, seq, status_ptr, self.ops._stream()), 'vosmem_wait_flags')
 
 
-class PeerExchange:
-    """Candidate exchange without a collective: every rank writes its local top-k lists into a symmetric (peer-mapped)
-    buffer, one device-side barrier tells the ranks that all lists are in place, and the merge kernel loads the other
-    ranks' lists over NVLink itself (vosmem_merge_topk_ptrs).  Two slots alternate between frames, so the single barrier
-    per frame also protects the slot that is overwritten two frames later."""
+class _Layout:
+    """Byte layout of one rank's exchange buffer (identical on every rank: peers address it by offset)."""
+    CONTROL = 4096          # list flags [2][16] u32 @0, output flags [2][16] u32 @128, tickets @256/@260, status @264
 
-    def __init__(self, hw: int, top_k: int, device, group):
-        import torch.distributed._symmetric_memory as symm
-        self.hw, self.k = hw, top_k
-        self.score_bytes = hw * top_k * 4
-        self.slot_bytes = hw * top_k * 12                      # fp32 scores + int64 global indices
-        self.buf = symm.empty(2 * self.slot_bytes, dtype=torch.uint8, device=device)
-        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.peer_base = [int(p) for p in self.handle.buffer_ptrs]
-        self.frame = 0
+    def __init__(self, world: int, per: int, rows: int, hw: int, with_output: bool):
+        self.world, self.per = world, per
+        self.list_bytes = per * EXCH_K * ENTRY                     # one source rank's lists for one owner
+        self.slot_bytes = world * self.list_bytes
+        self.lists0 = self.CONTROL
+        self.out0 = self.lists0 + 2 * self.slot_bytes
+        self.out_bytes = rows * hw * 4 if with_output else 0
+        self.total = self.out0 + 2 * self.out_bytes
 
-    def slot_views(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(score, index) views of this frame's slot in the local buffer: the selection writes straight into them."""
-        b = (self.frame & 1) * self.slot_bytes
-        score = self.buf[b:b + self.score_bytes].view(torch.float32).view(self.hw, self.k)
-        index = self.buf[b + self.score_bytes:b + self.slot_bytes].view(torch.int64).view(self.hw, self.k)
-        return score, index
+    def lists(self, slot: int, src: int = 0) -> int:
+        return self.lists0 + slot * self.slot_bytes + src * self.list_bytes
 
-    def peer_lists(self) -> Tuple[List[int], List[int]]:
-        b = (self.frame & 1) * self.slot_bytes
-        return [p + b for p in self.peer_base], [p + b + self.score_bytes for p in self.peer_base]
+    def list_flag(self, slot: int, src: int = 0) -> int:
+        return (slot * 16 + src) * 4
 
-    def barrier_and_advance(self):
-        self.handle.barrier(channel=0)
-        self.frame += 1
+    def out_flag(self, slot: int, src: int = 0) -> int:
+        return 128 + (slot * 16 + src) * 4
+
+    def out(self, slot: int) -> int:
+        return self.out0 + slot * self.out_bytes
+
+    ticket_push, ticket_slice, status = 256, 260, 264
 
 
 class ShardedLongTermReadout:
     """Long-term memory bank sharded along N across `world` ranks (BASELINE.json configs[3])."""
 
-    launches_per_match = 4  # select_tc (packs the query), merge_splits, merge_lists, softmax_readout
+    launches_per_match = 3      # select_tc (packs the query), merge_push, softmax_readout<exchange>  (+2 with gather)
 
     def __init__(self, config: dict, rank: int, world: int, device, backend=None, group=None):
         self.top_k = config['top_k']
-        # 'nccl': one all-gather of the packed candidates; 'peer': symmetric-memory buffers + NVLink loads inside the
-        # merge kernel (CUDA backend only)
-        self.exchange = str(config.get('vosmem_exchange', 'nccl')).lower()
+        # 'peer': stores + flags over NVLink inside the kernels (CUDA backend only); 'nccl': one all-to-all of the lists
+        self.exchange = str(config.get('vosmem_exchange', 'peer' if backend is None else 'nccl')).lower()
         assert self.exchange in ('nccl', 'peer')
-        self._peer = None
-        # 'n' (north_star): the key axis is sharded, candidates are exchanged.  'queries' (the control of SURVEY section
-        # 8e): every rank keeps the whole bank and serves HW / world query rows end to end; the only collective is the
-        # all-gather of the rows x HW readout slices.
+        # 'n' (north_star): keys sharded, candidates exchanged, readout sharded over the queries.  'queries' (the control
+        # of SURVEY section 8e): every rank keeps the whole bank and serves HW / world query rows end to end.
         self.shard = str(config.get('vosmem_shard', 'n')).lower()
         assert self.shard in ('n', 'queries')
         self.rank, self.world, self.device, self.group = rank, world, device, group
@@ -134,14 +177,129 @@ class ShardedLongTermReadout:
         self.n_total = 0
         self.rows = 0
         self.lo = self.hi = 0
+        self.seq = 0
+        self._buf = None         # (layout, local tensor, [base pointer of every rank])
+        self._send = None
 
+    # ------------------------------------------------------------------------------------------------
     def load_long_term(self, key, shrinkage, value) -> None:
         """key 1 x CK x N, shrinkage 1 x 1 x N, value n_obj x CV x N: the whole bank; this rank keeps keys [lo, hi)."""
         self.n_total = key.shape[-1]
         self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank) if self.shard == 'n' else (0, self.n_total)
         if self.hi > self.lo:
             self.backend.load_keys(key[:, :, self.lo:self.hi], shrinkage[:, :, self.lo:self.hi])
+        else:   # an empty shard still answers every query with an empty list: one key that can never be selected
+            self.backend.load_keys(key[:, :, :0], shrinkage[:, :, :0])
         self.rows = self.backend.load_values(value)
+
+    def _buffers(self, hw: int, with_output: bool):
+        """Exchange buffer of this rank, peer-mapped on every rank in 'peer' mode (allocated on first use: collective)."""
+        per = query_slices(hw, self.world)
+        if self._buf is not None and self._buf[0].per == per and (self._buf[0].out_bytes > 0 or not with_output):
+            return self._buf
+        lay = _Layout(self.world, per, self.rows, hw, with_output)
+        if self.exchange == 'peer' and self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(lay.total, dtype=torch.uint8, device=self.device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            bases = [int(p) for p in handle.buffer_ptrs]
+            handle.barrier(channel=0)            # every rank's buffer is zeroed before anyone pushes into it
+            self._handle = handle
+        else:
+            buf = self.backend.new_buffer(lay.total)
+            bases = [buf.data_ptr()] * self.world
+        self._buf = (lay, buf, bases)
+        return self._buf
+
+    def query_range(self, hw: int) -> Tuple[int, int]:
+        per = query_slices(hw, self.world)
+        return min(hw, self.rank * per), min(hw, (self.rank + 1) * per)
+
+    # ------------------------------------------------------------------------------------------------
+    def match(self, query_key, selection, events=None, gather: bool = True) -> torch.Tensor:
+        """query_key / selection: 1 x CK x h x w.  gather=True -> rows x HW (the full readout on every rank);
+        gather=False -> rows x (q_hi - q_lo), this rank's query slice (``query_range``).
+        events (optional, for bench.py): [after local select + push, after exchange + readout, after gather]."""
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        qk = query_key.flatten(start_dim=2)[0]
+        qe = selection.flatten(start_dim=2)[0] if selection is not None else None
+        if self.shard == 'queries':
+            return self._match_query_sharded(qk, qe, hw, events, gather)
+        be, k, G, r = self.backend, self.top_k, self.world, self.rank
+        peer = self.exchange == 'peer' and G > 1
+        lay, buf, bases = self._buffers(hw, with_output=gather and peer)
+        per = lay.per
+        q_lo, q_hi = self.query_range(hw)
+        self.seq += 1
+        seq, slot = self.seq, self.seq & 1
+        me = bases[r]
+
+        # ---- 1. local selection, lists pushed to the owners ----
+        if peer:
+            dst = [bases[d] + lay.lists(slot, r) for d in range(G)]
+            flags = [bases[d] + lay.list_flag(slot, r) for d in range(G)]
+            be.select_push(qk, qe, k, self.lo, per, G, r, dst, flags, seq, me + lay.ticket_push)
+        else:
+            if self._send is None or self._send.numel() != lay.slot_bytes:
+                self._send = be.new_buffer(lay.slot_bytes)
+            send = self._send
+            dst = [send.data_ptr() + d * lay.list_bytes for d in range(G)]
+            be.select_push(qk, qe, k, self.lo, per, G, r, dst, None, seq, me + lay.ticket_push, send=send)
+        if events is not None:
+            events[0].record()
+
+        # ---- 2. exchange (collective mode only) + merge of the `world` lists + softmax + readout of the own slice ----
+        lists_ptr, flags_ptr, lists = me + lay.lists(slot), me + lay.list_flag(slot), None
+        if not peer:
+            if G > 1:
+                lists = buf[lay.lists(slot):lay.lists(slot) + lay.slot_bytes]
+                dist.all_to_all_single(lists, send, group=self.group)        # [owner][per][K] -> [source][per][K]
+            else:
+                lists, lists_ptr = send, send.data_ptr()
+            flags_ptr = None
+        n_q = q_hi - q_lo
+        if gather and peer:
+            full = buf[lay.out(slot):lay.out(slot) + lay.out_bytes].view(torch.float32).view(self.rows, hw)
+        else:
+            full = torch.empty((self.rows, hw if gather else max(n_q, 1)), dtype=torch.float32, device=qk.device)
+        mine = full[:, q_lo:q_hi] if gather else full[:, :n_q]
+        if n_q > 0:
+            be.exchange_readout(lists_ptr, G, per * EXCH_K, 0, flags_ptr, seq, me + lay.status, n_q, k, self.rows,
+                                self.n_total, mine, lists=lists)
+        if events is not None:
+            events[1].record()
+        if not gather:
+            if events is not None:
+                events[2].record()
+            return mine
+
+        # ---- 3. replicate the slices ----
+        if G > 1 and peer:
+            if n_q > 0:
+                others = [d for d in range(G) if d != r]
+                be.push_slice(mine, [bases[d] + lay.out(slot) + q_lo * 4 for d in others], hw,
+                              [bases[d] + lay.out_flag(slot, r) for d in others], seq, me + lay.ticket_slice)
+            mask = sum(1 << s for s in range(G) if s != r and min(hw, s * per) < min(hw, (s + 1) * per))
+            if mask:                # ranks whose query slice is empty push nothing
+                be.wait_flags(me + lay.out_flag(slot), mask, seq, me + lay.status)
+        elif G > 1:
+            part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
+            part[:, :n_q] = mine
+            gathered = self._all_gather(part)                                   # world x rows x per
+            full = gathered.permute(1, 0, 2).reshape(self.rows, G * per)[:, :hw]
+        if events is not None:
+            events[2].record()
+        return full
+
+    def check_status(self) -> None:
+        """Raise if a flag wait timed out on the device (synchronises)."""
+        if self._buf is None:
+            return
+        lay, buf, _ = self._buf
+        if int(buf[lay.status:lay.status + 4].view(torch.int32).item()) != 0:
+            raise RuntimeError('sharded readout: a wait for another rank\'s flag timed out')
 
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -151,80 +309,33 @@ class ShardedLongTermReadout:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return out.view((self.world,) + tuple(t.shape))
 
-    def match(self, query_key, selection, events=None) -> torch.Tensor:
-        """query_key / selection: 1 x CK x h x w  ->  rows x HW (full readout on every rank).
-        events (optional, for bench.py): [after local select, after exchange + merge, after readout]."""
-        h, w = query_key.shape[-2:]
-        hw = h * w
-        qk = query_key.flatten(start_dim=2)[0]
-        qe = selection.flatten(start_dim=2)[0] if selection is not None else None
-        k = self.top_k
-        if self.shard == 'queries':
-            return self._match_query_sharded(qk, qe, hw, events)
-        peer = None
-        if self.exchange == 'peer' and self.world > 1 and hasattr(self.backend, 'merge_ptrs'):
-            if self._peer is None or self._peer.hw != hw:
-                self._peer = PeerExchange(hw, k, qk.device, self.group)      # collective: every rank gets here together
-            peer = self._peer
-        out = peer.slot_views() if peer is not None else None
-        if self.hi > self.lo:
-            score, index = self.backend.select(qk, qe, k, self.lo, out) if out is not None else \
-                self.backend.select(qk, qe, k, self.lo)
-        elif out is not None:   # empty shard: contributes no candidates
-            score, index = out[0].fill_(float('-inf')), out[1].fill_(-1)
-        else:
-            score = torch.full((hw, k), float('-inf'), dtype=torch.float32, device=qk.device)
-            index = torch.full((hw, k), -1, dtype=torch.int64, device=qk.device)
-        if events is not None:
-            events[0].record()
-        if peer is not None:
-            # ---- exchange fused into the merge: barrier, then the merge kernel reads every rank's list in place ----
-            score_ptrs, index_ptrs = peer.peer_lists()
-            peer.barrier_and_advance()
-            g_score, g_index = self.backend.merge_ptrs(score_ptrs, index_ptrs, hw, k)
-            all_s = None
-        # ---- the one exchange step: all-gather of the local top-k candidates (one message: fp32 score bits and
-        #      the global index as int32 pairs, HW * k * 8 bytes per rank) ----
-        elif self.world == 1:
-            all_s, all_i = score.unsqueeze(0), index.unsqueeze(0)
-        else:
-            packed = torch.stack((score.view(torch.int32), index.to(torch.int32)))     # 2 x HW x k
-            gathered = self._all_gather(packed)                                          # world x 2 x HW x k
-            all_s = gathered[:, 0].contiguous().view(torch.float32)
-            all_i = gathered[:, 1].to(torch.int64)
-        if all_s is not None:
-            g_score, g_index = self.backend.merge(all_s, all_i)            # identical on every rank
-        if events is not None:
-            events[1].record()
-        # ---- readout: values are replicated, so every rank reads out all query rows itself.  (Slicing the query
-        #      rows over the ranks and all-gathering rows x HW fp32 afterwards was measured slower at 2 GPUs: 24 us
-        #      for the half readout + 56 us for the 16.7 MB gather against 35 us for the whole readout.) ----
-        out = torch.empty((self.rows, hw), dtype=torch.float32, device=qk.device)
-        self.backend.readout(g_score, g_index, self.rows, self.n_total, out=out)
-        if events is not None:
-            events[2].record()
-        return out
-
-    def _match_query_sharded(self, qk, qe, hw, events):
-        """Query rows [qlo, qhi) of this rank against the whole bank, then one all-gather of the readout slices."""
-        per = -(-hw // self.world)
-        per = -(-per // 16) * 16                                   # slice starts stay 64-byte aligned
-        qlo, qhi = min(hw, self.rank * per), min(hw, (self.rank + 1) * per)
+    def _match_query_sharded(self, qk, qe, hw, events, gather):
+        """Control: query rows [q_lo, q_hi) of this rank against the whole bank (one all-gather of the slices if asked)."""
+        be, k = self.backend, self.top_k
+        per = query_slices(hw, self.world)
+        q_lo, q_hi = self.query_range(hw)
+        n_q = q_hi - q_lo
         part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
-        if qhi > qlo:
-            sl_k = qk[:, qlo:qhi].contiguous()
-            sl_e = qe[:, qlo:qhi].contiguous() if qe is not None else None
-            score, index = self.backend.select(sl_k, sl_e, self.top_k, 0)
+        if n_q > 0:
+            sl_k = qk[:, q_lo:q_hi].contiguous()
+            sl_e = qe[:, q_lo:q_hi].contiguous() if qe is not None else None
+            if self._send is None or self._send.numel() != n_q * EXCH_K * ENTRY + 64:
+                self._send = be.new_buffer(n_q * EXCH_K * ENTRY + 64)
+            base = self._send.data_ptr()
+            be.select_push(sl_k, sl_e, k, 0, n_q, 1, 0, [base], None, 1, base + n_q * EXCH_K * ENTRY, send=self._send)
             if events is not None:
                 events[0].record()
-                events[1].record()
-            self.backend.readout(score, index, self.rows, self.n_total, out=part[:, :qhi - qlo])
+            be.exchange_readout(base, 1, n_q * EXCH_K, 0, None, 1, None, n_q, k, self.rows, self.n_total, part[:, :n_q],
+                                lists=self._send)
         elif events is not None:
             events[0].record()
+        if events is not None:
             events[1].record()
+        if not gather or self.world == 1:
+            if events is not None:
+                events[2].record()
+            return part[:, :n_q] if not gather else part[:, :hw]
+        gathered = self._all_gather(part)                               # world x rows x per
         if events is not None:
             events[2].record()
-        if self.world == 1:
-            return part[:, :hw]
-        gathered = self._all_gather(part)                               # world x rows x per
         return gathered.permute(1, 0, 2).reshape(self.rows, self.world * per)[:, :hw]
