@@ -541,7 +541,7 @@ def pcie_ceiling(ctx, nbytes, copies=20):
 
 
 # ------------------------------------------------------------------------------------------------
-def measure_sharded(ctx, K, W, exchange, shard, want_e2e, want_parity=True, gather=False):
+def measure_sharded(ctx, K, W, exchange, shard, want_e2e, want_parity=True, gather=False, share=True):
     """BASELINE configs[3]: one LVOS-scale long-term bank sharded along N over the ranks (strong scaling).
     Every rank also holds the whole bank for the in-run 1-GPU unsharded reference time (rank 0 alone runs it)."""
     import vos_e_sam_b200 as vos
@@ -554,7 +554,8 @@ def measure_sharded(ctx, K, W, exchange, shard, want_e2e, want_parity=True, gath
     gl = torch.Generator().manual_seed(1234 + 4)     # same bank on every rank; each keeps its shard
     k, s, _ = synth.keys(gl, n)
     v = torch.randn(n_obj, CV, n, generator=gl)
-    engine = ShardedLongTermReadout(xmem_config(vosmem_exchange=exchange, vosmem_shard=shard), rank, world, dev)
+    engine = ShardedLongTermReadout(xmem_config(vosmem_exchange=exchange, vosmem_shard=shard, vosmem_share_thresholds=share),
+                                    rank, world, dev)
     engine.load_long_term(k, s, v)
     gq = torch.Generator().manual_seed(1234 + 40)
     pool = 4
@@ -592,6 +593,7 @@ def measure_sharded(ctx, K, W, exchange, shard, want_e2e, want_parity=True, gath
                stage_us=dict(select_and_push=statistics.mean(sel_ms) * 1e3, exchange_and_readout=statistics.mean(rd_ms) * 1e3,
                              gather=statistics.mean(ga_ms) * 1e3, step_median=statistics.median(step_ms) * 1e3),
                exchange=exchange, shard=shard, gather_output=gather, scaling='strong',
+               thresholds_shared_across_ranks=bool(share and exchange == 'peer' and world > 1),
                result='every rank holds the readout of its query slice' if not gather else 'full readout replicated on every rank',
                config=workload_config('lvos_sharded', world))
 
@@ -691,7 +693,7 @@ def run_ours(args, rank, world, local_rank):
     if args.workload == 'lvos_sharded':
         # the sharded workload as the headline of this run (builder's sweeps); the default run carries it as `sharded`
         with ClockSampler(local_rank) as clocks:
-            sh = measure_sharded(ctx, K, W, args.exchange, args.shard, want_e2e=True, gather=args.gather)
+            sh = measure_sharded(ctx, K, W, args.exchange, args.shard, want_e2e=True, gather=args.gather, share=not args.no_share)
         if rank == 0:
             line = dict(metric=METRIC, value=sh['value'], unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=sh['ms_per_step'],
                         higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16 values, ~fp32 scores (bf16 hi/lo x3)',
@@ -761,6 +763,7 @@ def main():
     ap.add_argument('--exchange', default='peer', choices=['nccl', 'peer'],
                     help='sharded bank: lists pushed into the owner\'s peer memory over NVLink, or one NCCL all-to-all')
     ap.add_argument('--gather', action='store_true', help='lvos_sharded: replicate the full readout on every rank')
+    ap.add_argument('--no-share', action='store_true', help='lvos_sharded: no thresholds shared across the ranks (A/B)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', 0))
@@ -776,7 +779,7 @@ def main():
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
                '--workload', args.workload, '--exchange', args.exchange, '--shard', args.shard] + \
               (['--no-cpu-baseline'] if args.no_cpu_baseline else []) + (['--headline-only'] if args.headline_only else []) + \
-              (['--gather'] if args.gather else [])
+              (['--gather'] if args.gather else []) + (['--no-share'] if args.no_share else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -205,6 +205,14 @@ typedef struct vosmem_push_desc {
                                             landed, or NULL                                                        */
   uint32_t seq;
   uint32_t *ticket;                      /* zero-initialised device word of this rank (last-CTA detection)         */
+  /* Optional (all NULL = off): thresholds shared across the ranks while the selection kernels run.  rank_pub[d] is a
+   * zero-initialised [world][round_up(HW, 128)] x 8-byte array in rank d's memory (peer-mapped for d != rank).  Every
+   * rank keeps writing, per query, a lower bound that world x (its candidate lists) x R of ITS keys reach into row
+   * `rank` of every array and reads the other rows of its own array, so that a query's threshold is backed by 33
+   * keys of the WHOLE bank: each rank then keeps ~33 / world candidates per query instead of 33, which takes the
+   * selection out of its append-bound regime.  Requires that all ranks issue the same sequence of calls on the
+   * workspaces they pass (their launch epochs must agree). */
+  void *rank_pub[VOSMEM_MAX_RANKS];
 } vosmem_push_desc;
 
 /* select (desc->index_base is ignored: push->index_base is applied) + merge of the split lists + push */

@@ -50,7 +50,8 @@ EXCH_K = 32
 
 class PushDesc(C.Structure):
     _fields_ = [('world', C.c_int), ('rank', C.c_int), ('per', C.c_int), ('index_base', i64), ('dst', vp * MAX_RANKS),
-                ('flag', vp * MAX_RANKS), ('seq', C.c_uint32), ('ticket', vp)]
+                ('flag', vp * MAX_RANKS), ('seq', C.c_uint32), ('ticket', vp),
+                ('rank_pub', vp * MAX_RANKS)]
 
 
 class ExchangeDesc(C.Structure):

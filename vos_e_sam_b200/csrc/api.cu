@@ -124,7 +124,8 @@ extern "C" int vosmem_workspace_status(const void *workspace, vosmem_stream_t st
 }
 
 // run the selection kernel(s) of `n` problems: leaves the per-split candidate lists in each problem's workspace
-static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub) {
+static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
+                         const PeerThresholds *peers = nullptr) {
   int path = 0, splits = MAX_SPLITS;
   for (int b = 0; b < n; ++b) {
     int rc = validate_select(d + b);
@@ -152,7 +153,9 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
     if (rc != VOSMEM_OK) return rc;
   }
   if (g_stage_events[1]) cudaEventRecord(g_stage_events[1], st);
-  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(d, ws, n, splits, st) : launch_select_simt(*d, ws[0], splits, st);
+  if (peers != nullptr && peers->world > 1)
+    VOSMEM_CHECK_ARG(path == VOSMEM_PATH_TCGEN05 && n == 1, "select: thresholds across ranks need the tcgen05 path, one problem");
+  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(d, ws, n, splits, st, peers) : launch_select_simt(*d, ws[0], splits, st);
   if (rc != VOSMEM_OK) return rc;
   if (g_stage_events[2]) cudaEventRecord(g_stage_events[2], st);
   return VOSMEM_OK;
@@ -160,8 +163,9 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
 
 namespace vosmem {
 // the selection stage alone, for the sharded path (exchange.cu): candidate lists stay in the workspace
-int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub) {
-  return run_selection(d, 1, st, ws, n_lists, n_pub);
+int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
+                           const PeerThresholds *peers) {
+  return run_selection(d, 1, st, ws, n_lists, n_pub, peers);
 }
 }  // namespace vosmem
 

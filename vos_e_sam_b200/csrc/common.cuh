@@ -172,6 +172,7 @@ struct Workspace {
   WsControl *ctl;              // control words (first 256 bytes)
   unsigned char *query_image;  // n_qtiles * QUERY_TILE_BYTES
   PubEntry *pub;               // pub_rows * hw_pad: lower bound published per (virtual split, query) by the current launch
+  PubEntry *pub2;              // the same for the (smaller) rank used when thresholds are shared across ranks
   CandEntry *cand;             // splits * hw_pad * CAND_SLOTS
   int *cand_count;             // splits * hw_pad
   int pub_rows;                // rows of `pub` (= splits_cap * LISTS_PER_SPLIT)
@@ -204,6 +205,7 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
   w.ctl = reinterpret_cast<WsControl *>(take(sizeof(WsControl)));
   w.query_image = take(n_qtiles * QUERY_TILE_BYTES);
   w.pub = reinterpret_cast<PubEntry *>(take(cap * hw_pad * 8));
+  w.pub2 = reinterpret_cast<PubEntry *>(take(cap * hw_pad * 8));
   w.pub_rows = (int)cap;
   w.cand = reinterpret_cast<CandEntry *>(take((int64_t)splits_cap(hw) * hw_pad * CAND_SLOTS * 8));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));
@@ -221,7 +223,15 @@ struct SelectPlan {
 
 int launch_pack_query(const float *qk, const float *qe, int ck, int hw, const Workspace &ws, cudaStream_t st);
 int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int splits, cudaStream_t st);
-int launch_select_tc(const vosmem_select_desc *d, const Workspace *ws, int n, int splits, cudaStream_t st);
+// Thresholds shared ACROSS ranks of an N-sharded bank (select_tc.cu, "Thresholds across ranks"): rank_pub[d] is the
+// [world][hw_pad] array of rank summaries in rank d's (peer-mapped) memory; row `rank` of every array is written by
+// this rank, the rows of the local array (rank_pub[rank]) are read.
+struct PeerThresholds {
+  int world = 1, rank = 0;
+  PubEntry *rank_pub[VOSMEM_MAX_RANKS] = {};
+};
+int launch_select_tc(const vosmem_select_desc *d, const Workspace *ws, int n, int splits, cudaStream_t st,
+                     const PeerThresholds *peers = nullptr);
 int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st);
 int choose_splits(int path, int hw, int64_t n_total, int batch = 1);

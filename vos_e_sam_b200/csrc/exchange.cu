@@ -51,13 +51,16 @@ __device__ __forceinline__ void signal_when_grid_done(uint32_t *ticket, uint32_t
 
 // One warp per query: merge the split lists of the local selection into the local top-k (merge.cuh), write the
 // VOSMEM_EXCH_K-entry exchange list (global key indices; unused slots {-inf, -1}) into the owner's buffer.
-__global__ void __launch_bounds__(256) merge_push_kernel(const __grid_constant__ PushArgs a) {
+// MB: split lists merged per batch (registers: 2 MB per lane; with few splits the small instantiation doubles the
+// resident warps of this latency-bound kernel).
+template <int MB>
+__global__ void __launch_bounds__(256, MB <= 4 ? 4 : 2) merge_push_kernel(const __grid_constant__ PushArgs a) {
   __shared__ float buf_s[8][MERGE_BUF];
   __shared__ int buf_i[8][MERGE_BUF];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   if (q < a.hw) {
-    const WarpTop32 top = merge_query(a.lists, q, buf_s[warp], buf_i[warp], lane);
+    const WarpTop32 top = merge_query<MB>(a.lists, q, buf_s[warp], buf_i[warp], lane);
     const bool have = lane < a.top_k && top.i != 0x7fffffff;
     const int owner = q / a.per, local = q - owner * a.per;
     const uint2 entry = make_uint2(__float_as_uint(have ? top.s : -INFINITY), have ? (uint32_t)(top.i + (int)a.index_base) : 0xffffffffu);
@@ -110,7 +113,8 @@ __global__ void wait_flags_kernel(const uint32_t *flags, uint32_t mask, uint32_t
 
 }  // namespace
 
-int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub);
+int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
+                           const PeerThresholds *peers);
 
 }  // namespace vosmem
 
@@ -129,7 +133,15 @@ extern "C" int vosmem_select_push(const vosmem_select_desc *select, const vosmem
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
   int n_lists = 1, n_pub = 1;
-  int rc = run_selection_for_push(select, st, &ws, n_lists, n_pub);
+  PeerThresholds peers;
+  peers.world = push->world;
+  peers.rank = push->rank;
+  bool shared = push->world > 1;
+  for (int r = 0; r < push->world; ++r) {
+    peers.rank_pub[r] = static_cast<PubEntry *>(push->rank_pub[r]);
+    shared = shared && push->rank_pub[r] != nullptr;
+  }
+  int rc = run_selection_for_push(select, st, &ws, n_lists, n_pub, shared ? &peers : nullptr);
   if (rc != VOSMEM_OK) return rc;
   PushArgs a{};
   a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(select->hw, TQ), ws.ctl};
@@ -145,7 +157,8 @@ extern "C" int vosmem_select_push(const vosmem_select_desc *select, const vosmem
   }
   a.seq = push->seq;
   a.ticket = push->ticket;
-  merge_push_kernel<<<(select->hw + 7) / 8, 256, 0, st>>>(a);
+  if (n_lists <= 4) merge_push_kernel<4><<<(select->hw + 7) / 8, 256, 0, st>>>(a);
+  else merge_push_kernel<MERGE_MAX_SPLITS><<<(select->hw + 7) / 8, 256, 0, st>>>(a);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }

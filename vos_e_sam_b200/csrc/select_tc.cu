@@ -39,6 +39,18 @@
 //           splits then has at least 33 keys at or above it.  Published values carry the launch epoch (PubEntry),
 //           so nothing has to be reset between launches.  With S splits running concurrently this tracks the
 //           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
+//
+// Thresholds across ranks (N-sharded bank, vosmem_select_push with rank_pub set).  Sharding the key axis over G ranks
+// would make every rank collect ITS OWN best 33 per query -- G times the appends of a single pass, which is what bounds
+// this kernel on short key streams.  Instead the ranks share thresholds while their kernels run.  Every virtual split
+// publishes a second bound, its R2-th best with R2 = ceil(33 / (G x virtual splits)) <= R (the tracker holds it anyway);
+// the CTA of split 0 of every query tile keeps pushing the rank's summary (min over its virtual splits of those) into row
+// `rank` of every rank's peer-mapped summary array (8-byte st.global over NVLink, a few KB per microsecond), and every
+// CTA's refresher takes the minimum over the G rows of its LOCAL array: a bound backed by 33 keys of the whole bank.
+// The threshold used is the larger of that and the rank's own bound (above), so a rank never does worse than alone --
+// whatever the skew between the ranks' kernels -- and towards ~33 / G kept candidates per query once the rows flow.
+// Rows carry the launch epoch, which all ranks advance in step (same call sequence on the engine's workspaces); a
+// row that is missing or stale reads as -inf, i.e. no cross-rank bound yet.
 #include <cfloat>
 
 #include "common.cuh"
@@ -103,6 +115,7 @@ struct TcArgs {
   int hw, hw_pad, splits;
   const float *qk, *qe;   // query key / selection, CK x hw fp32 (qe may be NULL: isotropic)
   PubEntry *pub;          // [virtual splits][hw_pad] published lower bound per (virtual split, query): see "Thresholds"
+  PubEntry *pub2;         // the same for rank R2 ("Thresholds across ranks"; only written / read when world > 1)
   WsControl *ctl;         // device-side launch epoch (tags this launch's published values), departure counter, error flags
   CandEntry *cand;
   int *cand_count;
@@ -111,8 +124,11 @@ struct TcArgs {
 
 struct TcBatch {   // kernel parameter: one TcArgs per problem (blockIdx.z)
   TcArgs p[MAX_BATCH];
+  // thresholds across ranks (problem 0 only; world == 1: off)
+  int world, rank, r2;
+  PubEntry *rank_pub[VOSMEM_MAX_RANKS];   // [d]: rank d's [world][hw_pad] summary array; [rank] is the local one
 };
-static_assert(sizeof(TcBatch) <= 3584, "kernel parameter space");
+static_assert(sizeof(TcBatch) <= 4000, "kernel parameter space");
 
 // The query operand lives in tensor memory: 8 columns per K=16 step, [hi steps 0-7 | lo steps 0-7 | tail].
 // One tcgen05.cp (128 rows x 256 bits) per step from the packed shared-memory image.
@@ -460,6 +476,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // (a stale value is still a valid lower bound, so no ordering with the epilogue is needed)
     const int row0 = (warp - W_REFRESH) * (TQ / N_REFRESH);
     const PubEntry *pub_row = a.pub + qtile * TQ + row0 + lane;
+    const int world = batch.world, my_rank = batch.rank;
+    const bool pusher = world > 1 && blockIdx.y == 0;      // one CTA per query tile publishes the rank's summary
+    float pushed[RH];
+#pragma unroll
+    for (int h = 0; h < RH; ++h) pushed[h] = -INFINITY;
     for (int it = 0; *epi_done < EPI_WARPS; ++it) {
       float m[RH];
 #pragma unroll
@@ -469,6 +490,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
       else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, epoch, m);
       else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, epoch, m);
+      if (world > 1) {
+        // ---- thresholds across ranks: g = this rank's summary (min over its virtual splits of their R2-th best);
+        //      push it when it rose, fold in the other ranks' rows, use the larger of the local and the global bound ----
+        const int64_t col = qtile * TQ + row0 + lane;
+        const PubEntry *pub2_row = a.pub2 + qtile * TQ + row0 + lane;
+        float g[RH];
+#pragma unroll
+        for (int h = 0; h < RH; ++h) g[h] = INFINITY;
+        if (vsplits <= 2) refresh_pass<2>(pub2_row, vsplits, a.hw_pad, epoch, g);
+        else if (vsplits <= 4) refresh_pass<4>(pub2_row, vsplits, a.hw_pad, epoch, g);
+        else refresh_pass<RB>(pub2_row, vsplits, a.hw_pad, epoch, g);
+        if (pusher && (it < 8 || (it & 3) == 0)) {
+#pragma unroll
+          for (int h = 0; h < RH; ++h) {
+            if (g[h] > pushed[h]) {
+              pushed[h] = g[h];
+              for (int d = 0; d < world; ++d)
+                if (d != my_rank) pub_store(batch.rank_pub[d] + (int64_t)my_rank * a.hw_pad + col + 32 * h, g[h], epoch);
+            }
+          }
+        }
+        const PubEntry *mine_rows = batch.rank_pub[my_rank];
+        for (int s0 = 0; s0 < world; s0 += 8) {      // eight ranks' rows in flight at a time
+          uint2 raw[8][RH];
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            const int ss = s0 + s < world ? s0 + s : my_rank;   // (own row is never used: the fresh local value stands in)
+#pragma unroll
+            for (int h = 0; h < RH; ++h)
+              raw[s][h] = __ldcg(reinterpret_cast<const uint2 *>(mine_rows + (int64_t)ss * a.hw_pad + col + 32 * h));
+          }
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+#pragma unroll
+            for (int h = 0; h < RH; ++h)
+              if (s0 + s < world && s0 + s != my_rank)
+                g[h] = fminf(g[h], raw[s][h].y == epoch ? __uint_as_float(raw[s][h].x) : -INFINITY);
+        }
+#pragma unroll
+        for (int h = 0; h < RH; ++h) m[h] = fmaxf(m[h], g[h]);
+      }
 #pragma unroll
       for (int h = 0; h < RH; ++h) tau_sh[row0 + lane + 32 * h] = m[h];
       if (it >= 16) __nanosleep(256);   // thresholds move fastest during the first tiles
@@ -529,11 +591,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     const int vsplit = blockIdx.y * HALVES + half;
     const bool live = qtile * TQ + row < a.hw;
     float tau = live ? -FLT_MAX : INFINITY;        // this thread's view of its query's threshold (shared one only)
-    float pub = -INFINITY;                         // what this thread has published so far
+    float pub = -INFINITY, pub2 = -INFINITY;       // what this thread has published so far (rank R / rank R2)
     float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
 #pragma unroll
     for (int u = 0; u < R; ++u) best[u] = -INFINITY;
     PubEntry *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
+    PubEntry *pub2_mine = a.pub2 + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
     long long t_wait = 0, t_scan = 0, t_post = 0;
     int *tile_ctr = reinterpret_cast<int *>(smem + SM_CTR) + quarter;
     int n_done = 0;      // tiles this warp has scanned
@@ -602,6 +665,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         if (best[R - 1] > pub) {
           pub = best[R - 1];
           pub_store(pub_mine + lane, pub, epoch);
+        }
+        if (batch.world > 1) {   // the R2-th best of the same tracker, for the bound shared across ranks
+          float b2 = best[0];
+#pragma unroll
+          for (int u = 1; u < R; ++u) b2 = (u < batch.r2) ? best[u] : b2;
+          if (b2 > pub2) {
+            pub2 = b2;
+            pub_store(pub2_mine + lane, pub2, epoch);
+          }
         }
         tau = fmaxf(tau, tau_sh[row]);
         unsigned mine = 0;
@@ -868,9 +940,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_tile_kernel(const unsigned
 
 thread_local long long *g_tc_debug = nullptr;  // set through vosmem_debug_set_timing_buffer (per host thread)
 
-int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, cudaStream_t st) {
+int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, cudaStream_t st,
+                     const PeerThresholds *peers) {
   VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "select(tcgen05): batch of %d problems outside [1, %d]", n, MAX_BATCH);
   TcBatch batch{};
+  batch.world = 1;
+  if (peers != nullptr && peers->world > 1) {
+    VOSMEM_CHECK_ARG(n == 1 && peers->world <= VOSMEM_MAX_RANKS && peers->rank >= 0 && peers->rank < peers->world,
+                     "select(tcgen05): thresholds across ranks: rank %d of %d, %d problems", peers->rank, peers->world, n);
+    batch.world = peers->world;
+    batch.rank = peers->rank;
+    for (int r = 0; r < peers->world; ++r) {
+      VOSMEM_CHECK_ARG(peers->rank_pub[r] != nullptr, "select(tcgen05): no summary array for rank %d", r);
+      batch.rank_pub[r] = peers->rank_pub[r];
+    }
+  }
   for (int b = 0; b < n; ++b) {
     const vosmem_select_desc &d = descs[b];
     const Workspace &ws = wss[b];
@@ -899,6 +983,7 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
     a.qk = d.query_key;
     a.qe = d.query_selection;
     a.pub = ws.pub;
+    a.pub2 = ws.pub2;
     a.ctl = ws.ctl;
     a.cand = ws.cand;
     a.cand_count = ws.cand_count;
@@ -906,8 +991,9 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
   }
   const vosmem_select_desc &d = descs[0];
   dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits, n);
-  // R * (virtual splits) >= 33 keys must stand behind a shared threshold
+  // R * (virtual splits) >= 33 keys must stand behind a shared threshold; R2 likewise over the lists of all ranks
   const int r = (33 + HALVES * splits - 1) / (HALVES * splits);
+  batch.r2 = (33 + HALVES * splits * batch.world - 1) / (HALVES * splits * batch.world);
   // the shared-memory opt-in is a per-device function attribute: set it on every launch (a host-side table lookup)
 #define VOSMEM_LAUNCH_TC(RR)                                                                                     \
   do {                                                                                                           \

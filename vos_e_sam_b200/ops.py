@@ -128,7 +128,8 @@ def age(life_count: Tensor, n: int) -> None:
 
 # ------------------------------------------------------------------------------------------------
 def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment], top_k: int, index_base: int,
-                 path: int, keep: list, slot: int = 0, d: Optional[N.SelectDesc] = None) -> N.SelectDesc:
+                 path: int, keep: list, slot: int = 0, d: Optional[N.SelectDesc] = None,
+                 workspace: Optional[Tensor] = None) -> N.SelectDesc:
     _need(qk, 'query_key')
     ck, hw = qk.shape
     qk = qk.contiguous()
@@ -154,7 +155,7 @@ def _select_desc(qk: Tensor, qe: Optional[Tensor], segments: Sequence[KeySegment
         g.begin, g.end = s.begin, s.end
     d.index_base = index_base
     d.path = path
-    ws = workspace_for(qk.device, ck, hw, slot)
+    ws = workspace if workspace is not None else workspace_for(qk.device, ck, hw, slot)   # caller-owned: already initialised
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     return d
 

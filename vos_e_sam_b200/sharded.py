@@ -88,21 +88,31 @@ class CudaBackend:
     def new_buffer(self, nbytes: int) -> torch.Tensor:
         return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
 
-    def select_push(self, qk, qe, top_k, index_base, per, world, rank, dst_ptrs, flag_ptrs, seq, ticket_ptr, send=None):
+    def workspace_bytes(self, ck: int, hw: int) -> int:
+        return int(self.N.lib.vosmem_workspace_bytes(ck, hw, 0))
+
+    def init_workspace(self, ws: torch.Tensor) -> None:
+        self.N.check(self.N.lib.vosmem_workspace_init(ws.data_ptr(), ws.numel(), self.ops._stream()), 'vosmem_workspace_init')
+
+    def select_push(self, qk, qe, top_k, index_base, per, world, rank, dst_ptrs, flag_ptrs, seq, ticket_ptr, send=None,
+                    workspace=None, rank_pub_ptrs=None):
         """Local selection over this rank's keys + push of every query's list to its owner (one C call, two launches).
-        `send`: the tensor behind dst_ptrs in collective mode (unused here: the kernel takes the raw addresses)."""
+        `send`: the tensor behind dst_ptrs in collective mode (unused here: the kernel takes the raw addresses).
+        `workspace`: the engine's own (peer-mapped) scratch; `rank_pub_ptrs`: every rank's threshold summary array
+        (thresholds shared across the ranks while the kernels run), or None."""
         N, ops = self.N, self.ops
         push = N.PushDesc()
         push.world, push.rank, push.per, push.index_base = world, rank, per, index_base
         for r in range(world):
             push.dst[r] = dst_ptrs[r]
             push.flag[r] = flag_ptrs[r] if flag_ptrs is not None else None
+            push.rank_pub[r] = rank_pub_ptrs[r] if rank_pub_ptrs is not None else None
         push.seq, push.ticket = seq, ticket_ptr
         keep: list = []
         if self.n_keys == 0:
             raise RuntimeError('CudaBackend.select_push: this rank\'s key shard is empty (use fewer ranks or a larger bank)')
         seg = [self.keys.key_segment(0, self.n_keys)]
-        sd = ops._select_desc(qk, qe, seg, top_k, 0, N.PATH_AUTO, keep)
+        sd = ops._select_desc(qk, qe, seg, top_k, 0, N.PATH_AUTO, keep, workspace=workspace)
         N.check(N.lib.vosmem_select_push(C.byref(sd), C.byref(push), ops._stream()), 'vosmem_select_push')
 
     def exchange_readout(self, lists_ptr, n_lists, list_stride, first_entry, flags_ptr, seq, status_ptr, n_q, top_k, rows,
@@ -134,11 +144,16 @@ class _Layout:
     """Byte layout of one rank's exchange buffer (identical on every rank: peers address it by offset)."""
     CONTROL = 4096          # list flags [2][16] u32 @0, output flags [2][16] u32 @128, tickets @256/@260, status @264
 
-    def __init__(self, world: int, per: int, rows: int, hw: int, with_output: bool):
+    def __init__(self, world: int, per: int, rows: int, hw: int, with_output: bool, ws_bytes: int = 0):
         self.world, self.per = world, per
+        self.hw_pad = -(-hw // 128) * 128
+        self.rank_pub0 = self.CONTROL                              # [world][hw_pad] x 8 B threshold summaries
+        self.rank_pub_bytes = -(-world * self.hw_pad * 8 // 256) * 256
+        self.ws0 = self.rank_pub0 + self.rank_pub_bytes            # the selection workspace (epochs in step across ranks)
+        self.ws_bytes = -(-ws_bytes // 256) * 256
         self.list_bytes = per * EXCH_K * ENTRY                     # one source rank's lists for one owner
         self.slot_bytes = world * self.list_bytes
-        self.lists0 = self.CONTROL
+        self.lists0 = self.ws0 + self.ws_bytes
         self.out0 = self.lists0 + 2 * self.slot_bytes
         self.out_bytes = rows * hw * 4 if with_output else 0
         self.total = self.out0 + 2 * self.out_bytes
@@ -172,6 +187,8 @@ class ShardedLongTermReadout:
         # of SURVEY section 8e): every rank keeps the whole bank and serves HW / world query rows end to end.
         self.shard = str(config.get('vosmem_shard', 'n')).lower()
         assert self.shard in ('n', 'queries')
+        # thresholds shared across the ranks while the selection kernels run ('peer' mode only; see vosmem.h)
+        self.share_thresholds = bool(config.get('vosmem_share_thresholds', True))
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.backend = backend if backend is not None else CudaBackend(device)
         self.n_total = 0
@@ -197,14 +214,18 @@ class ShardedLongTermReadout:
         per = query_slices(hw, self.world)
         if self._buf is not None and self._buf[0].per == per and (self._buf[0].out_bytes > 0 or not with_output):
             return self._buf
-        lay = _Layout(self.world, per, self.rows, hw, with_output)
-        if self.exchange == 'peer' and self.world > 1:
+        peer = self.exchange == 'peer' and self.world > 1
+        ws_bytes = self.backend.workspace_bytes(64, hw) if peer and hasattr(self.backend, 'workspace_bytes') else 0
+        lay = _Layout(self.world, per, self.rows, hw, with_output, ws_bytes)
+        if peer:
             import torch.distributed._symmetric_memory as symm
             buf = symm.empty(lay.total, dtype=torch.uint8, device=self.device)
             buf.zero_()
+            if ws_bytes:
+                self.backend.init_workspace(buf[lay.ws0:lay.ws0 + ws_bytes])
             handle = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
             bases = [int(p) for p in handle.buffer_ptrs]
-            handle.barrier(channel=0)            # every rank's buffer is zeroed before anyone pushes into it
+            handle.barrier(channel=0)            # every rank's buffer is initialised before anyone pushes into it
             self._handle = handle
         else:
             buf = self.backend.new_buffer(lay.total)
@@ -240,7 +261,10 @@ class ShardedLongTermReadout:
         if peer:
             dst = [bases[d] + lay.lists(slot, r) for d in range(G)]
             flags = [bases[d] + lay.list_flag(slot, r) for d in range(G)]
-            be.select_push(qk, qe, k, self.lo, per, G, r, dst, flags, seq, me + lay.ticket_push)
+            share = self.share_thresholds and lay.ws_bytes > 0 and qk.shape[0] == 64
+            be.select_push(qk, qe, k, self.lo, per, G, r, dst, flags, seq, me + lay.ticket_push,
+                           workspace=buf[lay.ws0:lay.ws0 + lay.ws_bytes] if lay.ws_bytes else None,
+                           rank_pub_ptrs=[bases[d] + lay.rank_pub0 for d in range(G)] if share else None)
         else:
             if self._send is None or self._send.numel() != lay.slot_bytes:
                 self._send = be.new_buffer(lay.slot_bytes)
