@@ -264,8 +264,8 @@ int vosmem_similarity_dense(const float *key, int64_t key_ld, const float *shrin
                             vosmem_stream_t stream);
 
 /* do_softmax (memory_util.py:41-65) over the key axis of an N x HW matrix (row pitch sim_ld).
- * top_k <= 0 means the max-subtracted dense softmax; usage (N) may be NULL.  affinity may alias
- * similarity (the reference's inplace=True). */
+ * top_k <= 0 means the max-subtracted dense softmax; 1 <= top_k <= 512 here (the fused per-frame calls above keep
+ * top_k <= VOSMEM_MAX_TOPK); usage (N) may be NULL.  affinity may alias similarity (the reference's inplace=True). */
 int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k, float *affinity,
                          int64_t aff_ld, float *usage, vosmem_stream_t stream);
 

@@ -23,18 +23,13 @@ torch.cuda.synchronize()
 N.lib.vosmem_debug_set_timing_buffer(None)
 d = dbg.view(-1, 32).cpu()
 d = d[(d != 0).any(1)]
-names = {0: 'prod_wait_empty', 1: 'mma_wait_tempty', 2: 'mma_wait_full', 3: 'mma_issue', 4: 'mma_total',
-         5: 'scan0_wait_tfull', 7: 'scan1_wait_tfull', 9: 'scan2_wait_tfull', 11: 'scan3_wait_tfull',
-         6: 'app0_relieve', 8: 'app1_relieve', 10: 'app2_relieve', 12: 'app3_relieve',
-         13: 'scan0_total', 16: 'scan0_scan', 17: 'scan0_post(wait ring)', 14: 'app0_total(incl handoff)', 26: 'app0_loop',
-         25: 'app0_wait_post', 18: 'app0_append(incl relieve)', 19: 'app0_active_groups', 20: 'app0_relieve_calls',
-         15: 'first_wait', 21: 'prologue', 22: 'cta_total'}
+names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls', 'prologue', 'cta_total']
 print('CTAs', d.shape[0])
 st = d[:, 15]
 print('warp1 first-tile wait cycles: mean', float(st.float().mean()), 'max', int(st.max()))
-for i, nm in sorted(names.items()):
+for i, nm in enumerate(names):
     col = d[:, i].float()
-    print(f'{nm:28s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f}')
+    print(f'{nm:16s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f}')
 
 start, end = d[:, 23].double(), d[:, 24].double()
 t0 = float(start.min())

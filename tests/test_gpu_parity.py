@@ -633,6 +633,23 @@ def test_peer_exchange_equals_nccl_exchange_on_two_gpus(vos):
     assert r.stdout.count('max |nccl - peer|') == 2 and r.stdout.count('vs unsharded') == 6
 
 
+def test_dense_softmax_twin_takes_large_top_k(vos):
+    """memory_util.do_softmax accepts any top_k (memory_util.py:46); the dense twin serves k up to 512 (the fused
+    per-frame path is limited to 32, checked at MemoryManager construction)."""
+    g = torch.Generator().manual_seed(23)
+    sim = torch.randn(1, 700, 50, generator=g) * 3
+    for k in (33, 64, 100):
+        aff, usage = vos.do_softmax(sim.cuda(), top_k=k, return_usage=True)
+        want, want_usage = orc.topk_affinity(sim, k, want_usage=True)
+        torch.testing.assert_close(aff.cpu(), want, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(usage.cpu(), want_usage, rtol=1e-4, atol=1e-6)
+    s2 = sim.cuda().clone()
+    assert vos.do_softmax(s2, top_k=64, inplace=True).data_ptr() == s2.data_ptr()
+    torch.testing.assert_close(s2.cpu(), orc.topk_affinity(sim, 64), rtol=1e-4, atol=1e-6)
+    with pytest.raises(ValueError, match='top_k'):
+        vos.MemoryManager(dict(hidden_dim=64, top_k=40, enable_long_term=False, enable_long_term_count_usage=False))
+
+
 def test_errors_are_loud(vos):
     g = torch.Generator().manual_seed(3)
     mk, ms, _ = synth.keys(g, 100)

@@ -98,6 +98,52 @@ __global__ void __launch_bounds__(1024) softmax_topk_dense_kernel(const float *s
   }
 }
 
+// Any top_k up to DENSE_MAX_TOPK (the fused per-frame path keeps k <= 32, one survivor per lane; this twin serves
+// memory_util.do_softmax callers with larger k): one warp per column extracts the next-best 32 in ceil(k / 32) passes
+// ("strictly worse than the last survivor" filters what earlier passes took), parks the survivors in shared memory
+// and only then overwrites the column -- so affinity may alias similarity.
+constexpr int DENSE_MAX_TOPK = 512;
+__global__ void __launch_bounds__(256) softmax_topk_any_kernel(const float *similarity, int64_t sim_ld, int64_t n, int hw,
+                                                               int top_k, float *affinity, int64_t aff_ld, float *usage) {
+  __shared__ float s_s[8][DENSE_MAX_TOPK];
+  __shared__ int s_i[8][DENSE_MAX_TOPK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= hw) return;
+  float bound_s = INFINITY;   // last survivor of the previous pass: later passes only take candidates worse than it
+  int bound_i = -1;
+  int kept = 0;
+  while (kept < top_k) {
+    WarpTop32 top;
+    top.init();
+    for (int64_t base = 0; base < n; base += 32) {
+      const int64_t i = base + lane;
+      float s = i < n ? similarity[i * sim_ld + q] : -INFINITY;
+      int idx = i < n ? (int)i : 0x7fffffff;
+      if (!better(bound_s, bound_i, s, idx)) { s = -INFINITY; idx = 0x7fffffff; }   // taken by an earlier pass
+      top.push(s, idx, lane);
+    }
+    const int take = min(32, top_k - kept);
+    if (lane < take) { s_s[warp][kept + lane] = top.s; s_i[warp][kept + lane] = top.i; }
+    bound_s = __shfl_sync(FULL, top.s, take - 1);
+    bound_i = __shfl_sync(FULL, top.i, take - 1);
+    kept += take;
+  }
+  __syncwarp();
+  const float m = s_s[warp][0];
+  float sum = 0.f;
+  for (int j = lane; j < top_k; j += 32) sum += s_i[warp][j] != 0x7fffffff ? expf(s_s[warp][j] - m) : 0.f;
+  sum = warp_sum(sum);
+  for (int64_t i = lane; i < n; i += 32) affinity[i * aff_ld + q] = 0.f;
+  __syncwarp();
+  for (int j = lane; j < top_k; j += 32) {
+    if (s_i[warp][j] == 0x7fffffff) continue;
+    const float w = expf(s_s[warp][j] - m) / sum;
+    affinity[(int64_t)s_i[warp][j] * aff_ld + q] = w;
+    if (usage) atomicAdd(usage + s_i[warp][j], w);
+  }
+}
+
 __global__ void __launch_bounds__(1024) softmax_full_dense_kernel(const float *similarity, int64_t sim_ld, int64_t n,
                                                                   int hw, float *affinity, int64_t aff_ld,
                                                                   float *usage) {
@@ -182,13 +228,15 @@ extern "C" int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int
                                     float *affinity, int64_t aff_ld, float *usage, vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(similarity && affinity, "vosmem_softmax_dense: null pointer");
   VOSMEM_CHECK_ARG(n >= 1 && hw >= 1, "vosmem_softmax_dense: n=%lld hw=%d", (long long)n, hw);
-  VOSMEM_CHECK_ARG(top_k <= VOSMEM_MAX_TOPK, "vosmem_softmax_dense: top_k=%d above %d", top_k, VOSMEM_MAX_TOPK);
+  VOSMEM_CHECK_ARG(top_k <= DENSE_MAX_TOPK, "vosmem_softmax_dense: top_k=%d above %d", top_k, DENSE_MAX_TOPK);
   VOSMEM_CHECK_ARG(top_k <= 0 || top_k <= n, "vosmem_softmax_dense: top_k=%d exceeds the %lld memory elements", top_k,
                    (long long)n);  // torch.topk raises here too (memory_util.py:46)
   cudaStream_t st = (cudaStream_t)stream;
   if (usage) VOSMEM_CUDA(cudaMemsetAsync(usage, 0, sizeof(float) * n, st));
   dim3 grid((hw + 31) / 32);
-  if (top_k > 0)
+  if (top_k > VOSMEM_MAX_TOPK)
+    softmax_topk_any_kernel<<<(hw + 7) / 8, 256, 0, st>>>(similarity, sim_ld, n, hw, top_k, affinity, aff_ld, usage);
+  else if (top_k > 0)
     softmax_topk_dense_kernel<<<grid, 1024, 0, st>>>(similarity, sim_ld, n, hw, top_k, affinity, aff_ld, usage);
   else
     softmax_full_dense_kernel<<<grid, 1024, 0, st>>>(similarity, sim_ld, n, hw, affinity, aff_ld, usage);

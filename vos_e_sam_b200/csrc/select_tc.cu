@@ -3,29 +3,25 @@
 // Replaces get_similarity + torch.topk of the reference (tracker/model/memory_util.py:7-39,46) for one
 // object group: the N x HW similarity matrix only ever exists as 128 x 64 fp32 tiles in tensor memory.
 //
-//   grid  = (query tiles of 128, N-splits, problems)   one CTA per SM (~229 KB shared memory), 20 warps;
+//   grid  = (query tiles of 128, N-splits, problems)   one CTA per SM (~229 KB shared memory), 12 warps;
 //           blockIdx.z selects one of up to MAX_BATCH independent problems (vosmem_match_batch)
-//   prologue         : warps 0-15 pack the CTA's 128-query tile ([-e | 2 q e | -sum e q^2] as bf16 hi / lo, the
+//   prologue         : warps 0-7 pack the CTA's 128-query tile ([-e | 2 q e | -sum e q^2] as bf16 hi / lo, the
 //                      shared-memory layout of a K-major no-swizzle UMMA operand) straight from the fp32 query key /
 //                      selection -- no separate packing kernel, no query image in global memory
-//   warp 16 producer : cp.async.bulk (TMA) of the streamed key tiles, mbarrier full/empty ring of STAGES stages
-//   warp 17 MMA      : copies the query operand into tensor memory once (tcgen05.cp), then per key tile
+//   warp 8  producer : cp.async.bulk (TMA) of the streamed key tiles, mbarrier full/empty ring of STAGES stages
+//   warp 9  MMA      : copies the query operand into tensor memory once (tcgen05.cp), then per key tile
 //                      25 tcgen05.mma (M128 N64 K16, A from TMEM, B from shared memory; bf16 hi/lo split
 //                      -> fp32) into one of ACC_BUFS accumulator buffers, tcgen05.commit -> mbarriers.  The whole
 //                      warp runs the loop convergently with uniform operands (see the kernel body)
-//   warps 18-19 refreshers: keep the per-query shared thresholds (below) fresh in shared memory
-//   The epilogue is split in two stages so that four warps per scheduler hide each other's latencies (with one
-//   stage per warp the epilogue ran at ~0.17 instructions per cycle and warp, bound by dependent-issue latency):
-//   warps 0-7  SCAN  : two per TMEM lane quarter, tiles handed out dynamically.  tcgen05.ld the tile (thread = query
-//                      row), maxima of the 8-column groups, threshold tracking / publication (below), one warp-wide OR
-//                      of "which groups hold a survivor for any lane" -> posted to the partner APPEND warp through a
-//                      two-deep shared-memory ring (mbarriers).  Never touches the candidate lists.
-//   warps 8-15 APPEND: partner (same quarter, same half) of a scan warp; owns one candidate list per query row
-//                      ("virtual split").  Re-reads ONLY the posted groups from tensor memory (tcgen05.ld x8),
-//                      appends every score at or above the thread's threshold to its private shared-memory list with
-//                      predicated stores (no branches), then frees the accumulator buffer.  When a list fills: drop
-//                      what fell below the (risen) threshold, thread-privately; only if that is not enough the warp
-//                      cuts lists to their best 32 with a bitonic network over packed 32-bit keys.
+//   warps 10-11 refreshers: keep the per-query shared thresholds (below) fresh in shared memory
+//   warps 0-7 epilogue: two warps per TMEM lane quarter, each with its own candidate lists and thresholds ("virtual
+//                      splits"); the tiles of a quarter are handed out dynamically to its two warps.
+//                      tcgen05.ld the tile (thread = query row), append every score above the
+//                      thread's threshold to a private shared-memory candidate list with predicated
+//                      stores (no branches).  Groups of 8 columns in which no lane has a survivor are
+//                      skipped with one warp-wide OR.  When a list fills: drop what fell below the
+//                      (risen) threshold, thread-privately; only if that is not enough the warp cuts
+//                      lists to their best 32 with a bitonic network over packed 32-bit keys.
 // Each CTA leaves <= 120 candidates per query in the exchange buffer; the merge (merge.cuh) finishes.
 //
 // Thresholds.  A query's threshold is only ever a LOWER bound of its true 32nd-best score, so no true
@@ -63,14 +59,12 @@ constexpr int STAGES = 3;
 constexpr int ACC_BUFS = 5;
 constexpr int TMEM_COLS = 512;            // 5 accumulator buffers (320 columns) + the query operand (136 columns)
 constexpr int TMEM_A = ACC_BUFS * TK;     // first column of the query operand: [hi 64 | lo 64 | tail 8]
-constexpr int HALVES = 2;                 // scan / append warp pairs per TMEM lane quarter = virtual splits (candidate list sets) per CTA
-constexpr int EPI_WARPS = 4 * HALVES;     // scan warps 0..7, append warps 8..15
-constexpr int W_APPEND = EPI_WARPS;
-constexpr int W_PRODUCER = 2 * EPI_WARPS, W_MMA = 2 * EPI_WARPS + 1, W_REFRESH = 2 * EPI_WARPS + 2;
+constexpr int HALVES = 2;                 // epilogue warps per TMEM lane quarter = virtual splits (candidate list sets) per CTA
+constexpr int EPI_WARPS = 4 * HALVES;
+constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_REFRESH = EPI_WARPS + 2;
 constexpr int N_REFRESH = 2;                         // refresher warps: each keeps TQ / N_REFRESH rows of tau_sh fresh
 constexpr int RH = TQ / 32 / N_REFRESH;              // rows per lane of a refresher warp
-constexpr int TC_THREADS = (2 * EPI_WARPS + 2 + N_REFRESH) * 32;   // 640
-constexpr int POST_DEPTH = 2;                        // scan -> append ring entries per warp pair
+constexpr int TC_THREADS = (EPI_WARPS + 2 + N_REFRESH) * 32;   // 384
 constexpr int CSLOTS = 60;             // candidate slots per (virtual split, query) in shared memory
 constexpr int CS_E = TQ + 1;           // 8-byte {score, local index} entries per slot row (+1: bank spread)
 constexpr int PRUNE_ABOVE = CSLOTS - 8;     // a list this long may overflow during the next 8 columns: relieve the warp
@@ -89,13 +83,12 @@ static_assert(2 * KEY_TILE_BYTES == QUERY_TILE_BYTES && STAGES >= 2, "query imag
 constexpr int LIST_BYTES = CSLOTS * CS_E * 8;
 constexpr int SM_CS = SM_K + STAGES * KEY_TILE_BYTES;   // HALVES candidate lists
 constexpr int SM_BAR = (SM_CS + HALVES * LIST_BYTES + 15) / 16 * 16;
-constexpr int N_BARS = 2 * STAGES + 2 * ACC_BUFS + 2 + 2 * EPI_WARPS * POST_DEPTH;
+constexpr int N_BARS = 2 * STAGES + 2 * ACC_BUFS + 2;
 constexpr int SM_TMEM = SM_BAR + N_BARS * 8;   // [0] TMEM base address, [1] epilogue warps finished
 constexpr int SM_TAU = SM_TMEM + 16;           // TQ floats: shared threshold per query row, kept fresh by the refresher
 constexpr int SM_NA = SM_TAU + TQ * 4;         // TQ ints: list length of warp set 0 per query row (for the hand-off)
 constexpr int SM_CTR = SM_NA + TQ * 4;          // 4 ints: next tile of each TMEM lane quarter (dynamic hand-out to its two warps)
-constexpr int SM_POST = SM_CTR + 16;            // EPI_WARPS x POST_DEPTH x {tile, active groups}: scan -> append ring
-constexpr int SM_TOTAL = SM_POST + EPI_WARPS * POST_DEPTH * 8;
+constexpr int SM_TOTAL = SM_CTR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget exceeded");
 
 constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TQ, TK);
@@ -315,37 +308,36 @@ __device__ __forceinline__ void refresh_pass(const PubEntry *pub_row, int vsplit
   }
 }
 
-// Warps 0-15 (512 threads): the query operand of this CTA's 128 queries, written in place as the shared-memory image
+// Warps 0-7 (256 threads): the query operand of this CTA's 128 queries, written in place as the shared-memory image
 // the tcgen05.cp copies expect.  Row y[q] = [-e | 2 q e | -sum_c e q^2] (memory_util.py:20-27; e = 1 and no last term
 // when there is no selection, :28-32), every fp32 entry as a bf16 (hi, lo) pair; 16-byte chunk order per row:
 // [y1_hi 0-7 | y2_hi 8-15 | y1_lo 16-23 | y2_lo 24-31 | tail 32 | 0 33], tail = (y3_hi, y3_lo, y3_hi, 0...).
-// Thread = (query row, quarter of the channels); loads are coalesced over the rows, stores are conflict-free.
-// red: 4 x TQ floats of scratch.
+// Thread = (query row, half of the channels); loads are coalesced over the rows, stores are conflict-free.
 __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsigned char *tile, float *red) {
-  const int r = threadIdx.x & (TQ - 1), csel = threadIdx.x >> 7;   // csel: channels [16 csel, 16 csel + 16)
+  const int r = threadIdx.x & (TQ - 1), hsel = threadIdx.x >> 7;
   const int q = qtile * TQ + r;
   const bool live = q < a.hw;
-  // all 32 loads are issued before the first use (no branch in between): rows past the end read the last query
+  // all 64 loads are issued before the first use (no branch in between): rows past the end read the last query
   // and are zeroed afterwards
-  float kk[16], ee[16];
+  float kk[32], ee[32];
   const int64_t col = live ? q : a.hw - 1;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) kk[j] = __ldg(a.qk + (int64_t)(csel * 16 + j) * a.hw + col);
+  for (int j = 0; j < 32; ++j) kk[j] = __ldg(a.qk + (int64_t)(hsel * 32 + j) * a.hw + col);
   if (a.qe) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ee[j] = __ldg(a.qe + (int64_t)(csel * 16 + j) * a.hw + col);
+    for (int j = 0; j < 32; ++j) ee[j] = __ldg(a.qe + (int64_t)(hsel * 32 + j) * a.hw + col);
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ee[j] = 1.f;
+    for (int j = 0; j < 32; ++j) ee[j] = 1.f;
   }
   if (!live) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) kk[j] = ee[j] = 0.f;
+    for (int j = 0; j < 32; ++j) kk[j] = ee[j] = 0.f;
   }
   float y3 = 0.f;
 #pragma unroll
-  for (int gg = 0; gg < 2; ++gg) {
-    const int g = csel * 2 + gg;
+  for (int gg = 0; gg < 4; ++gg) {
+    const int g = hsel * 4 + gg;
     uint32_t h1[4], l1[4], h2[4], l2[4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
@@ -368,10 +360,10 @@ __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsi
     *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 16 + g)) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
     *reinterpret_cast<uint4 *>(tile + image_offset<TQ>(r, 24 + g)) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
   }
-  red[csel * TQ + r] = y3;
-  asm volatile("bar.sync 6, 512;" ::: "memory");   // the sixteen packing warps
-  if (csel == 0) {
-    y3 = (red[r] + red[TQ + r]) + (red[2 * TQ + r] + red[3 * TQ + r]);
+  if (hsel == 1) red[r] = y3;
+  asm volatile("bar.sync 6, 256;" ::: "memory");   // the eight packing warps
+  if (hsel == 0) {
+    y3 += red[r];
     __nv_bfloat16 hi, lo;
     split_bf16(y3, hi, lo);
     const uint32_t h = __bfloat16_as_ushort(hi), l = __bfloat16_as_ushort(lo);
@@ -381,13 +373,10 @@ __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsi
   ptx::fence_proxy_async();   // the tcgen05.cp copies read the image through the async proxy
 }
 
-// scan -> append ring entry
-struct Post {
-  int tile;            // position in this CTA's key-tile stream, -1 = no more tiles
-  uint32_t active;     // bit g: the 8-column group g holds a score >= the scanning thread's threshold for some lane
-};
-
-template <int R>   // R = tracked / published rank per virtual split (see "Thresholds")
+// R = tracked / published rank per virtual split (see "Thresholds"); SHARED = thresholds across ranks (a separate
+// instantiation: the extra uniform state of that path costs the MMA warp its register -> uniform-register-free issue
+// loop, 39.4 against 37.4 us at the DAVIS shape, so single-GPU launches do not carry it)
+template <int R, bool SHARED>
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_constant__ TcBatch batch) {
   const TcArgs &a = batch.p[blockIdx.z];
   extern __shared__ __align__(128) unsigned char smem[];
@@ -397,12 +386,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   uint64_t *bar_tempty = bar_tfull + ACC_BUFS;
   uint64_t *bar_q = bar_tempty + ACC_BUFS;       // query image landed in shared memory
   uint64_t *bar_qdone = bar_q + 1;               // query operand copied to tensor memory: stages are free
-  uint64_t *bar_pfull = bar_qdone + 1;           // [EPI_WARPS][POST_DEPTH] scan warp posted a tile
-  uint64_t *bar_pempty = bar_pfull + EPI_WARPS * POST_DEPTH;   // append warp is done with the ring entry
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
   volatile uint32_t *epi_done = reinterpret_cast<volatile uint32_t *>(smem + SM_TMEM + 4);
   volatile float *tau_sh = reinterpret_cast<volatile float *>(smem + SM_TAU);
-  volatile Post *post = reinterpret_cast<volatile Post *>(smem + SM_POST);
 
   // warp index through a shuffle: provably warp-uniform, so the role branches below are known to be convergent and
   // the MMA warp's address arithmetic can live in uniform registers
@@ -425,7 +411,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     for (int i = 0; i < ACC_BUFS; ++i) { ptx::mbar_init(bar_tfull + i, 1); ptx::mbar_init(bar_tempty + i, 4); }
     ptx::mbar_init(bar_q, 1);
     ptx::mbar_init(bar_qdone, 1);
-    for (int i = 0; i < EPI_WARPS * POST_DEPTH; ++i) { ptx::mbar_init(bar_pfull + i, 1); ptx::mbar_init(bar_pempty + i, 1); }
     ptx::fence_barrier_init();
     *epi_done = 0;
     for (int i = 0; i < 4; ++i) reinterpret_cast<int *>(smem + SM_CTR)[i] = 0;
@@ -435,8 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  // (the candidate-list area is free until the first append: scratch for the packing reduction)
-  if (warp < 2 * EPI_WARPS) pack_query_tile(a, qtile, smem + SM_Q, reinterpret_cast<float *>(smem + SM_CS));
+  if (warp < EPI_WARPS) pack_query_tile(a, qtile, smem + SM_Q, reinterpret_cast<float *>(smem + SM_NA));
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -451,23 +435,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   constexpr uint32_t tmem_base = 0u;
   if (dbg && threadIdx.x == 0) dbg[21] = TICK() - t_entry;   // prologue
 
-  // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
-  const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
-            edge3 = (int)(a.tiles_total - 1 - g_lo);
-  // columns [jlo, jhi) of stream tile i are candidates (0, TK for all but the edge tiles)
-  auto tile_columns = [&](int i, int &jlo, int &jhi) {
-    jlo = 0;
-    jhi = TK;
-    if (i == edge0 || i == edge1 || i == edge2 || i == edge3) {
-      const int64_t g = g_lo + i;
-      const int sg = g >= a.seg[0].tiles;
-      const int64_t key0 = (sg ? a.seg[1].tile0 + (g - a.seg[0].tiles) : a.seg[0].tile0 + g) * TK;
-      const int64_t kb = a.seg[sg].begin, ke = a.seg[sg].end;
-      jlo = (int)max((int64_t)0, kb - key0);
-      jhi = (int)min((int64_t)TK, ke - key0);
-    }
-  };
-
   if (!tmem_ok) {
     // (no role runs; the candidate counts of this CTA's queries stay whatever they were: the caller sees the error flag)
   } else if (warp >= W_REFRESH) {
@@ -476,8 +443,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // (a stale value is still a valid lower bound, so no ordering with the epilogue is needed)
     const int row0 = (warp - W_REFRESH) * (TQ / N_REFRESH);
     const PubEntry *pub_row = a.pub + qtile * TQ + row0 + lane;
-    const int world = batch.world, my_rank = batch.rank;
-    const bool pusher = world > 1 && blockIdx.y == 0;      // one CTA per query tile publishes the rank's summary
+    const int world = SHARED ? batch.world : 1, my_rank = SHARED ? batch.rank : 0;
+    const bool pusher = SHARED && blockIdx.y == 0;         // one CTA per query tile publishes the rank's summary
     float pushed[RH];
 #pragma unroll
     for (int h = 0; h < RH; ++h) pushed[h] = -INFINITY;
@@ -490,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
       else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, epoch, m);
       else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, epoch, m);
-      if (world > 1) {
+      if (SHARED) {
         // ---- thresholds across ranks: g = this rank's summary (min over its virtual splits of their R2-th best);
         //      push it when it rose, fold in the other ranks' rows, use the larger of the local and the global bound ----
         const int64_t col = qtile * TQ + row0 + lane;
@@ -583,127 +550,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       }
       if (dbg && lane == 0) { dbg[1] = t_acc; dbg[2] = t_ld; dbg[3] = t_issue; dbg[4] = TICK() - t_begin; }
     }
-  } else if (warp < W_APPEND) {
-    // ===== SCAN warps 0-7: warp w owns TMEM lanes 32*(w%4).. ; the tiles of a quarter are handed out dynamically to
-    //       its two scan warps.  Group maxima, threshold tracking / publication, "which groups matter" -> append warp.
-    const int quarter = warp & 3, half = warp >> 2, pair = warp;   // pair = ring / list-set index (quarter, half)
-    const int row = quarter * 32 + lane;           // query row inside the tile
-    const int vsplit = blockIdx.y * HALVES + half;
-    const bool live = qtile * TQ + row < a.hw;
-    float tau = live ? -FLT_MAX : INFINITY;        // this thread's view of its query's threshold (shared one only)
-    float pub = -INFINITY, pub2 = -INFINITY;       // what this thread has published so far (rank R / rank R2)
-    float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
-#pragma unroll
-    for (int u = 0; u < R; ++u) best[u] = -INFINITY;
-    PubEntry *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
-    PubEntry *pub2_mine = a.pub2 + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
-    long long t_wait = 0, t_scan = 0, t_post = 0;
-    int *tile_ctr = reinterpret_cast<int *>(smem + SM_CTR) + quarter;
-    int n_done = 0;      // tiles this warp has scanned
-    int grabbed = 0;     // lane 0: the next tile of this warp (fetched one iteration ahead to hide the atomic)
-    if (lane == 0) grabbed = atomicAdd(tile_ctr, 1);
-    auto track = [&](float m) {   // sorted insertion, 2 R - 1 min / max
-#pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const float lo = fminf(best[u], m);
-        best[u] = fmaxf(best[u], m);
-        m = lo;
-      }
-    };
-    const long long t_begin = TICK();
-    for (int i = __shfl_sync(FULL, grabbed, 0);; i = __shfl_sync(FULL, grabbed, 0), ++n_done) {
-      const bool more = i < n_tiles;
-      uint32_t active = 0;
-      if (more) {
-        const int buf = i % ACC_BUFS;
-        const long long tw0 = TICK();
-        ptx::mbar_wait(bar_tfull + buf, (i / ACC_BUFS) & 1);
-        const long long tw1 = TICK();
-        t_wait += tw1 - tw0;
-        ptx::tc_fence_after();
-        int jlo, jhi;
-        tile_columns(i, jlo, jhi);
-        const bool first_exact = R >= 4 && n_done == 0;
-        float gm[TK / 8];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TK;
-        // two halves of 32 columns, one after the other: 32 live score registers instead of 64
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + 32 * hh, v);
-          ptx::tmem_ld_wait();
-          if (jlo > 0 || jhi < TK) {   // first / last tile of a candidate range: columns outside it never qualify
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (32 * hh + j < jlo || 32 * hh + j >= jhi) v[j] = 0xff800000u;  // -inf
-          }
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float m = __uint_as_float(v[g8 * 8]);
-#pragma unroll
-            for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, __uint_as_float(v[g8 * 8 + jj]));
-            gm[4 * hh + g8] = m;
-          }
-          if (first_exact) {   // first tile of this warp, few virtual splits: every score, so that the R-th best is
-                               // exact and can be published at once (8 group maxima cannot fill R >= 9 slots)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) track(__uint_as_float(v[j]));
-          }
-        }
-        if (lane == 0) grabbed = atomicAdd(tile_ctr, 1);
-        if (!first_exact) {
-          if (n_done < TRACK_TILES) {   // the group maxima, tile maxima after the first tiles
-#pragma unroll
-            for (int g8 = 0; g8 < TK / 8; ++g8) track(gm[g8]);
-          } else {
-            float tm = gm[0];
-#pragma unroll
-            for (int g8 = 1; g8 < TK / 8; ++g8) tm = fmaxf(tm, gm[g8]);
-            track(tm);
-          }
-        }
-        if (best[R - 1] > pub) {
-          pub = best[R - 1];
-          pub_store(pub_mine + lane, pub, epoch);
-        }
-        if (batch.world > 1) {   // the R2-th best of the same tracker, for the bound shared across ranks
-          float b2 = best[0];
-#pragma unroll
-          for (int u = 1; u < R; ++u) b2 = (u < batch.r2) ? best[u] : b2;
-          if (b2 > pub2) {
-            pub2 = b2;
-            pub_store(pub2_mine + lane, pub2, epoch);
-          }
-        }
-        tau = fmaxf(tau, tau_sh[row]);
-        unsigned mine = 0;
-#pragma unroll
-        for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] >= tau ? 1u : 0u) << g8;
-        active = __reduce_or_sync(FULL, mine);
-        t_scan += TICK() - tw1;
-      }
-      // ---- post to the append warp (two-deep ring); a tile of -1 ends its loop ----
-      {
-        const long long tp0 = TICK();
-        const int slot = n_done % POST_DEPTH;
-        if (lane == 0) {
-          ptx::mbar_wait(bar_pempty + pair * POST_DEPTH + slot, ((n_done / POST_DEPTH) & 1) ^ 1);
-          post[pair * POST_DEPTH + slot].tile = more ? i : -1;
-          post[pair * POST_DEPTH + slot].active = active;
-          ptx::mbar_arrive(bar_pfull + pair * POST_DEPTH + slot);   // release: the entry is visible to the waiter
-        }
-        __syncwarp();
-        t_post += TICK() - tp0;
-      }
-      if (!more) break;
-    }
-    if (dbg && lane == 0 && half == 0) {
-      dbg[5 + quarter * 2] = t_wait;
-      if (quarter == 0) { dbg[13] = TICK() - t_begin; dbg[16] = t_scan; dbg[17] = t_post; }
-    }
   } else {
-    // ===== APPEND warps 8-15: partner of scan warp (warp - 8); owns the candidate lists of its (quarter, half) =====
-    const int pair = warp - W_APPEND, quarter = pair & 3, half = pair >> 2;
+    // ===== epilogue: warps 0-7; warp w owns TMEM lanes 32*(w%4).. and drains the tiles with i % 2 == w/4 =====
+    const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;           // query row inside the tile
     Entry *cs = reinterpret_cast<Entry *>(smem + SM_CS + half * LIST_BYTES);
     volatile int *n_set0 = reinterpret_cast<volatile int *>(smem + SM_NA);
@@ -714,36 +563,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // Candidates are kept when score >= threshold: the shared threshold is the score of a real key, and with exact
     // ties at it (duplicated memory frames, uniform regions) a strict compare would drop keys the reference's
     // torch.topk returns.  The initial threshold is the lowest FINITE float, not -inf, so that masked columns
-    // (-inf) never qualify.  Rows past the last query (the tail of the last query tile) never keep anything: their
-    // operand is all zero, i.e. every key ties at score 0.
+    // (-inf) never qualify.
+    // Rows past the last query (the tail of the last query tile) never keep anything: their operand is all zero,
+    // i.e. every key ties at score 0.
     st.tau = qtile * TQ + row < a.hw ? -FLT_MAX : INFINITY;
     st.pub = -INFINITY;
+    float best[R];   // lower bounds of the R best scores of this warp set's keys, descending
+#pragma unroll
+    for (int u = 0; u < R; ++u) best[u] = -INFINITY;
     PubEntry *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
-    long long t_wait = 0, t_relieve = 0, t_first = 0, t_app = 0;
+    PubEntry *pub2_mine = a.pub2 + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
+    float pub2 = -INFINITY;   // what this thread has published for the cross-rank bound
+    long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
     int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
+    // Tiles are handed out dynamically to the two warps of a lane quarter (shared-memory counter), so a warp that is
+    // busy cutting its lists does not hold up the accumulator ring: its partner drains the tiles meanwhile.  Lists,
+    // thresholds and the tracker are per warp set and do not care which tiles they see.
+    int *tile_ctr = reinterpret_cast<int *>(smem + SM_CTR) + quarter;
+    int n_done = 0;      // tiles this warp has drained
+    int grabbed = 0;     // lane 0: the next tile of this warp (fetched one iteration ahead to hide the atomic)
+    if (lane == 0) grabbed = atomicAdd(tile_ctr, 1);
+    // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
+    const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
+              edge3 = (int)(a.tiles_total - 1 - g_lo);
     const long long t_begin = TICK();
-    for (int n_done = 0;; ++n_done) {
-      const int slot = n_done % POST_DEPTH;
-      const long long tw0 = TICK();
-      ptx::mbar_wait(bar_pfull + pair * POST_DEPTH + slot, (n_done / POST_DEPTH) & 1);
-      const int i = post[pair * POST_DEPTH + slot].tile;
-      const uint32_t active = post[pair * POST_DEPTH + slot].active;
-      const long long tw1 = TICK();
-      t_wait += tw1 - tw0;
-      if (i < 0) break;
+    for (int i = __shfl_sync(FULL, grabbed, 0); i < n_tiles; i = __shfl_sync(FULL, grabbed, 0), ++n_done) {
       const int buf = i % ACC_BUFS;
-      // (the scan warp saw this accumulator complete; this warp's own tensor-memory reads are ordered after its own
-      // observation of the same barrier phase)
+      const long long tw0 = TICK();
       ptx::mbar_wait(bar_tfull + buf, (i / ACC_BUFS) & 1);
+      t_wait += TICK() - tw0;
       ptx::tc_fence_after();
+      uint32_t v[TK];
+      {
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TK;
+        ptx::tmem_ld_32x32(taddr, v0);
+        ptx::tmem_ld_32x32(taddr + 32, v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v[j] = v0[j]; v[32 + j] = v1[j]; }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(bar_tempty + buf);  // accumulator buffer free again
+        grabbed = atomicAdd(tile_ctr, 1);
+      }
+      const long long tp1 = TICK();
+      t_ld += tp1 - tw0;
       st.tau = fmaxf(st.tau, tau_sh[row]);
+
+      // first / last tile of a candidate range: columns outside it never qualify
+      if (i == edge0 || i == edge1 || i == edge2 || i == edge3) {
+        const int64_t g = g_lo + i;
+        const int sg = g >= a.seg[0].tiles;
+        const int64_t key0 = (sg ? a.seg[1].tile0 + (g - a.seg[0].tiles) : a.seg[0].tile0 + g) * TK;
+        const int64_t kb = a.seg[sg].begin, ke = a.seg[sg].end;
+        if (key0 < kb || key0 + TK > ke) {
+          const int jlo = (int)max((int64_t)0, kb - key0), jhi = (int)min((int64_t)TK, ke - key0);
+#pragma unroll
+          for (int j = 0; j < TK; ++j)
+            if (j < jlo || j >= jhi) v[j] = 0xff800000u;  // -inf
+        }
+      }
+      // maxima of the 8-column groups: which groups hold a survivor for any lane
+      float gm[TK / 8];
+#pragma unroll
+      for (int g8 = 0; g8 < TK / 8; ++g8) {
+        float m = __uint_as_float(v[g8 * 8]);
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, __uint_as_float(v[g8 * 8 + jj]));
+        gm[g8] = m;
+      }
+      auto track = [&](float m) {   // sorted insertion, 2 R - 1 min / max
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const float lo = fminf(best[u], m);
+          best[u] = fmaxf(best[u], m);
+          m = lo;
+        }
+      };
+      if (R >= 4 && n_done == 0) {   // first tile of this warp, few virtual splits: every score, so that the R-th best is
+                                     // exact and can be published at once (8 group maxima cannot fill R >= 9 slots)
+#pragma unroll
+        for (int j = 0; j < TK; ++j) track(__uint_as_float(v[j]));
+      } else if (n_done < TRACK_TILES) {   // then the group maxima, tile maxima after the first tiles
+#pragma unroll
+        for (int g8 = 0; g8 < TK / 8; ++g8) track(gm[g8]);
+      } else {
+        float tm = gm[0];
+#pragma unroll
+        for (int g8 = 1; g8 < TK / 8; ++g8) tm = fmaxf(tm, gm[g8]);
+        track(tm);
+      }
+      if (best[R - 1] > st.pub) {
+        st.pub = best[R - 1];
+        pub_store(pub_mine + lane, st.pub, epoch);
+      }
+      if (SHARED) {   // the R2-th best of the same tracker, for the bound shared across ranks
+        float b2 = best[0];
+#pragma unroll
+        for (int u = 1; u < R; ++u) b2 = (u < batch.r2) ? best[u] : b2;
+        if (b2 > pub2) {
+          pub2 = b2;
+          pub_store(pub2_mine + lane, pub2, epoch);
+        }
+      }
       if (n_done == 0) {
-        // First tile of this warp pair: nothing is known yet and every score would be kept (and the lists cut by
-        // sorting several times before the thresholds bite).  The tile stays in tensor memory, so give the other
-        // virtual splits a bounded moment to publish the exact R-th best of their first tiles (the MMA warp keeps
-        // filling the other accumulator buffers meanwhile) and filter with the shared threshold.  On a timeout
-        // (e.g. a grid of several waves) the lists overflow and get sorted instead.
+        // First tile of this warp: nothing is known yet and every score would be kept (and the lists cut by sorting
+        // several times before the thresholds bite).  The tile sits in registers, so give the other virtual splits a
+        // bounded moment to publish the exact R-th best of their first tiles (the MMA warp keeps filling the other
+        // accumulator buffers meanwhile) and filter with the shared threshold.  On a timeout (e.g. a grid of
+        // several waves) the lists overflow and get sorted instead.
         const long long t0 = clock64();
         float shared = tau_sh[row];
         while (__any_sync(FULL, shared == -INFINITY) && clock64() - t0 < FIRST_WAIT_CYCLES) {
@@ -753,62 +685,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         st.tau = fmaxf(st.tau, shared);
         t_first = TICK() - t0;
       }
-      int jlo, jhi;
-      tile_columns(i, jlo, jhi);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TK;
+      unsigned mine = 0;
+#pragma unroll
+      for (int g8 = 0; g8 < TK / 8; ++g8) mine |= (gm[g8] >= st.tau ? 1u : 0u) << g8;
+      const unsigned active = __reduce_or_sync(FULL, mine);
+      const long long tp2 = TICK();
+      t_max += tp2 - tp1;
+
       const uint32_t li0 = (uint32_t)i * TK;
-      for (uint32_t todo = active; todo != 0; todo &= todo - 1) {   // warp-uniform: in steady state few groups are posted
-        const int g8 = __ffs(todo) - 1;
-        ++n_active;
-        uint32_t v[8];
-        ptx::tmem_ld_32x8(taddr + g8 * 8, v);
-        ptx::tmem_ld_wait();
-        if (jlo > 0 || jhi < TK) {
+#pragma unroll
+      for (int g8 = 0; g8 < TK / 8; ++g8) {
+        if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
+          ++n_active;
+          // slot addresses first (one select + add per column, each in a fresh register), then the predicated
+          // stores: no store waits for the previous store to release its address register
+          uint32_t slot[9];
+          slot[0] = st.off;
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
-            if (g8 * 8 + jj < jlo || g8 * 8 + jj >= jhi) v[jj] = 0xff800000u;  // -inf
-        }
-        // slot addresses first (one select + add per column, each in a fresh register), then the predicated
-        // stores: no store waits for the previous store to release its address register.  (Measured alternatives at
-        // the DAVIS shape, cycles per CTA: this 47 k; predicated in-place slot advance -- one instruction less per
-        // column -- 52 k; prefix tree over the eight increments + software-pipelined tensor-memory reads 57 k.)
-        uint32_t slot_a[9];
-        slot_a[0] = st.off;
+            slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) >= st.tau ? SS : 0u);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) slot_a[jj + 1] = slot_a[jj] + (__uint_as_float(v[jj]) >= st.tau ? SS : 0u);
-        const uint32_t li = li0 + g8 * 8;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          if (__uint_as_float(v[jj]) >= st.tau)
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot_a[jj]), "r"(v[jj]), "r"(li + jj) : "memory");
-        }
-        st.off = slot_a[8];
-        // Lists that could overflow during the next 8 columns.  The warp-uniform bound makes the real (voted) check
-        // rare: lists are short once the shared thresholds work.
-        len_bound += 8;
-        if (len_bound > PRUNE_ABOVE) {
-          len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = g8 * 8 + jj;
+            if (__uint_as_float(v[j]) >= st.tau)
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot[jj]), "r"(v[j]), "r"(li0 + j) : "memory");
+          }
+          st.off = slot[8];
+          // Lists that could overflow during the next 8 columns.  The warp-uniform bound makes the real (voted) check
+          // rare: lists are short once the shared thresholds work.
+          len_bound += 8;
           if (len_bound > PRUNE_ABOVE) {
-            const long long tr0 = TICK();
-            const float pub_before = st.pub;
-            st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
-            if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, epoch);
-            t_relieve += TICK() - tr0;
-            ++n_relieve;
             len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+            if (len_bound > PRUNE_ABOVE) {
+              const long long tr0 = TICK();
+              const float pub_before = st.pub;
+              st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
+              if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, epoch);
+              t_relieve += TICK() - tr0;
+              ++n_relieve;
+              len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+            }
           }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(bar_tempty + buf);                            // accumulator buffer free again
-        ptx::mbar_arrive(bar_pempty + pair * POST_DEPTH + slot);       // ring entry free again
-      }
-      t_app += TICK() - tw1;
+      t_app += TICK() - tp2;
     }
     __syncwarp();
-    if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warps retire
+    if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warp retire
     const long long t_loop = TICK() - t_begin;
 
     // ---- hand the surviving candidates to the merge: both sets of a query share one exchange row, set 0 first.
@@ -855,9 +778,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       }
     }
     if (dbg && lane == 0 && half == 0) {
+      dbg[5 + quarter * 2] = t_wait;
       dbg[6 + quarter * 2] = t_relieve;
-      if (quarter == 0) { dbg[14] = TICK() - t_begin; dbg[18] = t_app; dbg[19] = n_active; dbg[20] = n_relieve; dbg[25] = t_wait; dbg[26] = t_loop; }
+      if (quarter == 0) { dbg[13] = t_loop; dbg[14] = TICK() - t_begin; }
       if (quarter == 1) dbg[15] = t_first;
+      if (quarter == 0) { dbg[16] = t_ld; dbg[17] = t_max; dbg[18] = t_app; dbg[19] = n_active; dbg[20] = n_relieve; }
     }
   }
 
@@ -997,8 +922,13 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
   // the shared-memory opt-in is a per-device function attribute: set it on every launch (a host-side table lookup)
 #define VOSMEM_LAUNCH_TC(RR)                                                                                     \
   do {                                                                                                           \
-    VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
-    select_tc_kernel<RR><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                                 \
+    if (batch.world > 1) {                                                                                       \
+      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+      select_tc_kernel<RR, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                     \
+    } else {                                                                                                     \
+      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+      select_tc_kernel<RR, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                    \
+    }                                                                                                            \
   } while (0)
   if (r <= 1) VOSMEM_LAUNCH_TC(1);
   else if (r == 2) VOSMEM_LAUNCH_TC(2);

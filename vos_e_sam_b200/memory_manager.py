@@ -33,9 +33,19 @@ _PATHS = {'auto': N.PATH_AUTO, 'simt': N.PATH_SIMT, 'tcgen05': N.PATH_TCGEN05}
 class MemoryManager:
     """Manages working, long-term and sensory memory and the working -> long-term transition."""
 
+    @staticmethod
+    def _checked_top_k(config):
+        """The fused per-frame path holds one survivor per lane of a warp: top_k <= 32 (XMem ships 30, config.yaml:8).
+        Checked here rather than at the first match_memory; memory_util.do_softmax (the dense twin) takes up to 512."""
+        top_k = int(config['top_k'])
+        if not 1 <= top_k <= N.MAX_TOPK:
+            raise ValueError(f'vos_e_sam_b200.MemoryManager: top_k={top_k} outside [1, {N.MAX_TOPK}] (the fused readout keeps '
+                             f'one survivor per warp lane; see INTEGRATION.md "Limits")')
+        return top_k
+
     def __init__(self, config):
         self.hidden_dim = config['hidden_dim']
-        self.top_k = config['top_k']
+        self.top_k = self._checked_top_k(config)
 
         self.enable_long_term = config['enable_long_term']
         self.enable_long_term_usage = config['enable_long_term_count_usage']
@@ -65,7 +75,7 @@ class MemoryManager:
     def update_config(self, config):
         self.reset_config = True
         self.hidden_dim = config['hidden_dim']
-        self.top_k = config['top_k']
+        self.top_k = self._checked_top_k(config)
 
         assert self.enable_long_term == config['enable_long_term'], 'cannot update this'
         assert self.enable_long_term_usage == config['enable_long_term_count_usage'], 'cannot update this'

@@ -310,7 +310,11 @@ def similarity_dense(key: Tensor, shrinkage: Optional[Tensor], qk: Tensor, qe: O
 
 def softmax_dense(similarity: Tensor, top_k: Optional[int], inplace: bool, want_usage: bool):
     """similarity N x HW -> affinity N x HW [, usage N]."""
+    given = similarity
     similarity, sim_ld = _rows_2d(_need(similarity, 'similarity'), 'similarity')
+    if inplace and similarity.data_ptr() != given.data_ptr():
+        raise RuntimeError('softmax_dense(inplace=True) needs a similarity whose last dimension is contiguous '
+                           '(the kernel would otherwise update a copy)')
     n, hw = similarity.shape
     aff = similarity if inplace else torch.empty((n, hw), dtype=torch.float32, device=similarity.device)
     aff_ld = sim_ld if inplace else hw
