@@ -650,6 +650,27 @@ def test_dense_softmax_twin_takes_large_top_k(vos):
         vos.MemoryManager(dict(hidden_dim=64, top_k=40, enable_long_term=False, enable_long_term_count_usage=False))
 
 
+def test_bounded_banks_never_move(vos):
+    """With the XMem bounds known (max_mid_term_frames, max_long_term_elements) both banks are allocated once: the
+    device pointers the kernels (and any captured graph) hold stay valid over growth, consolidation and eviction."""
+    z = load('lifecycle_evict.npz')
+    cfg = lifecycle_config(z)
+    m = vos.MemoryManager(cfg)
+    ptrs = []
+
+    def on_match(i, got):
+        w, l = m.work_mem, m.long_mem
+        ptrs.append((w._k.buf.data_ptr(), w._image.data_ptr() if w._image is not None else 0, w._groups[0].shadow.data_ptr(),
+                     l._k.buf.data_ptr() if l.engaged() else None,
+                     l._groups[0].shadow.data_ptr() if l.engaged() else None))
+    results = replay_lifecycle(z, m, device='cuda', on_match=on_match)
+    assert m.long_mem.engaged() and len(results) > 20
+    assert len({p[:3] for p in ptrs}) == 1, 'working-memory buffers moved'
+    assert len({p[3:] for p in ptrs if p[3] is not None}) == 1, 'long-term buffers moved'
+    for i, got, want in results:
+        assert orc.rel_err(got.cpu(), want) < TOL_BF16, f'event {i}'
+
+
 def test_errors_are_loud(vos):
     g = torch.Generator().manual_seed(3)
     mk, ms, _ = synth.keys(g, 100)

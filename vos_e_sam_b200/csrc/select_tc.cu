@@ -445,9 +445,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     const PubEntry *pub_row = a.pub + qtile * TQ + row0 + lane;
     const int world = SHARED ? batch.world : 1, my_rank = SHARED ? batch.rank : 0;
     const bool pusher = SHARED && blockIdx.y == 0;         // one CTA per query tile publishes the rank's summary
-    float pushed[RH];
+    float pushed[RH], across[RH];   // last summary pushed / last bound obtained across the ranks
 #pragma unroll
-    for (int h = 0; h < RH; ++h) pushed[h] = -INFINITY;
+    for (int h = 0; h < RH; ++h) pushed[h] = across[h] = -INFINITY;
     for (int it = 0; *epi_done < EPI_WARPS; ++it) {
       float m[RH];
 #pragma unroll
@@ -457,9 +457,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
       else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, epoch, m);
       else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, epoch, m);
-      if (SHARED) {
+      if (SHARED && (it < 8 || (it & 3) == 0)) {
         // ---- thresholds across ranks: g = this rank's summary (min over its virtual splits of their R2-th best);
-        //      push it when it rose, fold in the other ranks' rows, use the larger of the local and the global bound ----
+        //      push it when it rose, fold in the other ranks' rows, use the larger of the local and the global bound.
+        //      Every fourth pass after the start: these bounds move slowly, the local ones must stay fresh ----
         const int64_t col = qtile * TQ + row0 + lane;
         const PubEntry *pub2_row = a.pub2 + qtile * TQ + row0 + lane;
         float g[RH];
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         if (vsplits <= 2) refresh_pass<2>(pub2_row, vsplits, a.hw_pad, epoch, g);
         else if (vsplits <= 4) refresh_pass<4>(pub2_row, vsplits, a.hw_pad, epoch, g);
         else refresh_pass<RB>(pub2_row, vsplits, a.hw_pad, epoch, g);
-        if (pusher && (it < 8 || (it & 3) == 0)) {
+        if (pusher) {
 #pragma unroll
           for (int h = 0; h < RH; ++h) {
             if (g[h] > pushed[h]) {
@@ -496,7 +497,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
                 g[h] = fminf(g[h], raw[s][h].y == epoch ? __uint_as_float(raw[s][h].x) : -INFINITY);
         }
 #pragma unroll
-        for (int h = 0; h < RH; ++h) m[h] = fmaxf(m[h], g[h]);
+        for (int h = 0; h < RH; ++h) across[h] = fmaxf(across[h], g[h]);
+      }
+      if (SHARED) {
+#pragma unroll
+        for (int h = 0; h < RH; ++h) m[h] = fmaxf(m[h], across[h]);
       }
 #pragma unroll
       for (int h = 0; h < RH; ++h) tau_sh[row0 + lane + 32 * h] = m[h];

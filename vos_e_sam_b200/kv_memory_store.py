@@ -33,8 +33,9 @@ def _round_up(x: int, m: int) -> int:
 class _Grow:
     """A [lead..., capacity] fp32 buffer with a logical length on the last axis."""
 
-    def __init__(self, lead: tuple, device, fill: float = 0.0):
+    def __init__(self, lead: tuple, device, fill: float = 0.0, min_capacity: int = 0):
         self.lead, self.device, self.fill = lead, device, fill
+        self.min_capacity = min_capacity            # first allocation is at least this large (KeyValueMemoryStore.reserve)
         self.buf = torch.empty(lead + (0,), dtype=torch.float32, device=device)
         self.n = 0
 
@@ -45,7 +46,7 @@ class _Grow:
     def reserve(self, total: int) -> bool:
         if total <= self.capacity:
             return False
-        cap = _round_up(max(total, 2 * self.capacity, MIN_CAPACITY), KEY_TILE)
+        cap = _round_up(max(total, 2 * self.capacity, MIN_CAPACITY, self.min_capacity), KEY_TILE)
         new = torch.empty(self.lead + (cap,), dtype=torch.float32, device=self.device)
         if self.n:
             new[..., :self.n].copy_(self.buf[..., :self.n])
@@ -83,9 +84,9 @@ class _Grow:
 class _ValueGroup:
     """Values of one object group: fp32 n_g x CV x N (reference layout) + the row-per-element shadow."""
 
-    def __init__(self, n_obj: int, cv: int, device, shadow_dtype):
+    def __init__(self, n_obj: int, cv: int, device, shadow_dtype, min_capacity: int = 0):
         self.n_obj, self.cv = n_obj, cv
-        self.ref = _Grow((n_obj, cv), device)
+        self.ref = _Grow((n_obj, cv), device, min_capacity=min_capacity)
         self.shadow_dtype = shadow_dtype
         self.shadow = torch.empty((0, n_obj * cv), dtype=shadow_dtype, device=device)
 
@@ -137,6 +138,14 @@ class KeyValueMemoryStore:
         self._groups: List[_ValueGroup] = []
         self.obj_groups: List[List[int]] = []
         self.all_objects: List[int] = []
+        self._min_capacity = 0
+
+    def reserve(self, n_elements: int) -> None:
+        """Size every buffer that is allocated from now on for at least `n_elements` memory elements.  With the bank's
+        bound known up front (working memory: max_mid_term_frames + 1 frames; long-term: max_long_term_elements) the
+        buffers are allocated once and never move, so device pointers captured in a CUDA graph or a descriptor stay
+        valid over add / sieve / eviction (the reference re-concatenates the bank on every add: kv_memory_store.py:49-56)."""
+        self._min_capacity = max(self._min_capacity, int(n_elements))
 
     # ---- packed key image -----------------------------------------------------------------------
     def _sync_image(self, begin: int) -> None:
@@ -160,12 +169,13 @@ class KeyValueMemoryStore:
         device, m = key.device, key.shape[2]
         first = self._k is None
         if first:
-            self._k = _Grow((key.shape[0], key.shape[1]), device)
-            self._s = _Grow((key.shape[0], 1), device) if shrinkage is not None else None
-            self._e = _Grow((key.shape[0], key.shape[1]), device) if selection is not None else None
+            mc = self._min_capacity
+            self._k = _Grow((key.shape[0], key.shape[1]), device, min_capacity=mc)
+            self._s = _Grow((key.shape[0], 1), device, min_capacity=mc) if shrinkage is not None else None
+            self._e = _Grow((key.shape[0], key.shape[1]), device, min_capacity=mc) if selection is not None else None
             if self.count_usage:
-                self._use = _Grow((key.shape[0], 1), device)
-                self._life = _Grow((key.shape[0], 1), device)
+                self._use = _Grow((key.shape[0], 1), device, min_capacity=mc)
+                self._life = _Grow((key.shape[0], 1), device, min_capacity=mc)
         begin = self._k.n
         self._k.append(key)
         if shrinkage is not None and self._s is not None:
@@ -190,7 +200,7 @@ class KeyValueMemoryStore:
                 self._groups[gi].append(value[group])
             if remaining:
                 new_group = list(remaining)
-                vg = _ValueGroup(len(new_group), value.shape[1], device, self.value_dtype)
+                vg = _ValueGroup(len(new_group), value.shape[1], device, self.value_dtype, self._min_capacity)
                 vg.append(value[new_group])
                 self._groups.append(vg)
                 self.obj_groups.append(new_group)
@@ -205,7 +215,7 @@ class KeyValueMemoryStore:
                 if gi < self.num_groups:
                     self._groups[gi].append(gv)
                 else:
-                    vg = _ValueGroup(gv.shape[0], gv.shape[1], device, self.value_dtype)
+                    vg = _ValueGroup(gv.shape[0], gv.shape[1], device, self.value_dtype, self._min_capacity)
                     vg.append(gv)
                     self._groups.append(vg)
 

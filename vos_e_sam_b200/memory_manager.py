@@ -201,6 +201,13 @@ class MemoryManager:
                 # frames -> memory elements
                 self.min_work_elements = self.min_mt_frames * self.HW
                 self.max_work_elements = self.max_mt_frames * self.HW
+                # both banks are bounded (memory_manager.py:184-190): allocate them once, so that their device
+                # pointers never move (graphs / descriptors stay valid).  Unbounded test configurations keep growing
+                # geometrically.
+                if self.max_work_elements + self.HW <= 1 << 20:
+                    self.work_mem.reserve(self.max_work_elements + self.HW)
+                if self.max_long_elements + self.num_prototypes <= 1 << 20:
+                    self.long_mem.reserve(self.max_long_elements + self.num_prototypes)
 
         key = key.flatten(start_dim=2)
         shrinkage = shrinkage.flatten(start_dim=2)
