@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VOSMEM_ABI_VERSION 2
+#define VOSMEM_ABI_VERSION 3
 
 typedef void *vosmem_stream_t; /* cudaStream_t */
 
@@ -213,9 +213,15 @@ typedef struct vosmem_push_desc {
    * selection out of its append-bound regime.  Requires that all ranks issue the same sequence of calls on the
    * workspaces they pass (their launch epochs must agree). */
   void *rank_pub[VOSMEM_MAX_RANKS];
+  /* Two candidate segments ([long-term shard | working-memory shard] of a sharded MemoryManager): local candidate i
+   * becomes global index  i + index_base  for i < seg0_len  and  i - seg0_len + index_base1  otherwise.
+   * seg0_len < 0: one base (index_base) for every candidate. */
+  int64_t seg0_len;
+  int64_t index_base1;
 } vosmem_push_desc;
 
-/* select (desc->index_base is ignored: push->index_base is applied) + merge of the split lists + push */
+/* select (desc->index_base is ignored: push->index_base is applied) + merge of the split lists + push.  A rank
+ * whose segments are all empty (fewer 64-key tiles than ranks) pushes empty lists and still raises its flags. */
 int vosmem_select_push(const vosmem_select_desc *select, const vosmem_push_desc *push, vosmem_stream_t stream);
 
 typedef struct vosmem_exchange_desc {

@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 N.lib.vosmem_debug_set_timing_buffer(None)
 d = dbg.view(-1, 32).cpu()
 d = d[(d != 0).any(1)]
-names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls', 'prologue', 'cta_total']
+names = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'e0_wait', 'e0_relieve', 'e1_wait', 'e1_relieve', 'e2_wait', 'e2_relieve', 'e3_wait', 'e3_relieve', 'e0_loop', 'e0_total', 'first_wait', 'e0_ld(incl wait)', 'e0_groupmax', 'e0_append(incl relieve)', 'e0_active_groups', 'e0_relieve_calls', 'prologue', 'cta_total', 'g_entry', 'g_exit', 'x0_vote_wait', 'x1_group_loop', 'e0_tiles']
 print('CTAs', d.shape[0])
 st = d[:, 15]
 print('warp1 first-tile wait cycles: mean', float(st.float().mean()), 'max', int(st.max()))

@@ -53,7 +53,7 @@ def test_struct_layouts_match_the_header(native):
 
 def test_host_side_layout_helpers(native):
     lib = native.lib
-    assert lib.vosmem_abi_version() == 2
+    assert lib.vosmem_abi_version() == 3
     # 64 keys per tile; 34 sixteen-byte chunks per key (16 hi + 16 lo + 2 tail)
     assert lib.vosmem_key_image_bytes(64, 64) == 64 * 34 * 16
     assert lib.vosmem_key_image_bytes(64, 65) == 2 * 64 * 34 * 16

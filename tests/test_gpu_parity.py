@@ -6,6 +6,9 @@ k-th and (k+1)-th similarity exceeds 1e-3; readout / usage agree within 1e-2 rel
 ``oracle.rel_err``).  With fp32 value storage the readout is held to 1e-4.
 """
 import math
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -136,6 +139,52 @@ def test_select_redundant_video(vos, path):
     score, index = vos.ops.select_topk(dev(qk).flatten(2)[0], dev(qe).flatten(2)[0], [store.key_segment(0, 6 * hw)], 30,
                                        path=p)
     check_selection(score, index, oracle_sim64(mk, ms, qk, qe), 30, f'{path} redundant')
+
+
+@pytest.mark.parametrize('n,h,w', [(40000, 40, 60), (65536, 68, 120)])
+def test_select_ascending_stream_overflows_every_list(vos, n, h, w):
+    """Worst case for the streaming selection: the shrinkage falls along the key axis, so every query's similarity RISES
+    along the stream and nearly every tile brings new best candidates -- the candidate lists overflow over and over
+    (cooperative cuts to the best 32) and, with group candidates, the per-list score logs wrap (flip_log: hundreds of
+    appends per list when a CTA streams 512 tiles).  Results must still be the oracle's (checked on 256 sampled queries)."""
+    g = torch.Generator().manual_seed(77 + n)
+    mk, _, _ = synth.keys(g, n)
+    ms = torch.linspace(60.0, 1.0, n).view(1, 1, n)
+    qk, qe = synth.query(g, h, w)
+    store = vos.KeyValueMemoryStore(count_usage=False)
+    store.add(dev(mk), [torch.zeros(1, 8, n, device='cuda')], dev(ms), None, None)
+    score, index = vos.ops.select_topk(dev(qk).flatten(2)[0], dev(qe).flatten(2)[0], [store.key_segment(0, n)], 30,
+                                       path=vos.N.PATH_TCGEN05)
+    torch.cuda.synchronize()
+    cols = torch.randperm(h * w, generator=g)[:256]
+    sim64 = oracle_sim64(mk, ms, qk.flatten(2)[:, :, cols].unsqueeze(-1), qe.flatten(2)[:, :, cols].unsqueeze(-1))
+    index, score = index.cpu()[cols], score.cpu()[cols]
+    # scores reach ~ -60 * 64 / 8: the error of the bf16 hi / lo split is relative, so the gap that decides a query and
+    # the score tolerance scale with the magnitude of its k-th score
+    top = torch.topk(sim64, k=31, dim=1)
+    scale = top.values[0, 29].abs().clamp(min=1.0)
+    decided = (top.values[0, 29] - top.values[0, 30]) > GAP * scale
+    same = orc.index_sets_equal(index.t(), top.indices[0, :30])
+    assert float(decided.float().mean()) > 0.5
+    assert not bool((decided & ~same).any()), f'{int((decided & ~same).sum())} of {int(decided.sum())} decided queries differ'
+    got = score.t().double()
+    want = torch.gather(sim64[0], 0, index.t().clamp(min=0))
+    assert float(((got - want).abs() / scale).max()) < 2e-3
+
+
+def test_group_candidate_mode_in_a_child_process(vos):
+    """VOSMEM_TC_CANDIDATES=groups (8-key group candidates + expansion in the merge, select_tc.cu / merge.cuh) is read
+    once per process: run the selection, tie, overflow, graph-replay and full-size match tests again in a child."""
+    if os.environ.get('VOSMEM_TEST_CHILD'):
+        pytest.skip('already the child')
+    env = dict(os.environ, VOSMEM_TC_CANDIDATES='groups', VOSMEM_TEST_CHILD='1')
+    pick = ('select_topk_vs_oracle or ascending or every_rank or two_segments or redundant or exact_ties or '
+            'davis_shape or davis5_full or replayed or batch_equals or sharded_engine')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-m', 'gpu', '-k', pick,
+                        '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout
 
 
 @pytest.mark.parametrize('path', ['simt', 'tcgen05'])

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libvosmem.so')
 
 OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, BF16 = 0, 1
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 MAX_TOPK = 32
@@ -51,7 +51,7 @@ EXCH_K = 32
 class PushDesc(C.Structure):
     _fields_ = [('world', C.c_int), ('rank', C.c_int), ('per', C.c_int), ('index_base', i64), ('dst', vp * MAX_RANKS),
                 ('flag', vp * MAX_RANKS), ('seq', C.c_uint32), ('ticket', vp),
-                ('rank_pub', vp * MAX_RANKS)]
+                ('rank_pub', vp * MAX_RANKS), ('seg0_len', i64), ('index_base1', i64)]
 
 
 class ExchangeDesc(C.Structure):

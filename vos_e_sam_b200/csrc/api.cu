@@ -3,7 +3,10 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "merge.cuh"
 
 namespace vosmem {
 
@@ -36,6 +39,17 @@ int choose_splits(int path, int hw, int64_t n_total, int batch) {
   if (s < 1) s = 1;
   if (s > cap) s = cap;
   return (int)s;
+}
+
+// Candidate granularity of the tcgen05 selection (select_tc.cu): single keys (default) or 8-key groups
+// (VOSMEM_TC_CANDIDATES=groups).  Both are parity-tested; the measurements that keep single keys the default are in
+// DESIGN.md section 3.1.  Read once per process.
+static bool tc_group_candidates() {
+  static const bool groups = [] {
+    const char *e = getenv("VOSMEM_TC_CANDIDATES");
+    return e != nullptr && strcmp(e, "groups") == 0;
+  }();
+  return groups;
 }
 
 static int resolve_path(const vosmem_select_desc &d) {
@@ -97,7 +111,7 @@ extern "C" int64_t vosmem_key_image_bytes(int ck, int64_t capacity) {
 extern "C" int64_t vosmem_workspace_bytes(int ck, int hw, int64_t n_keys) {
   (void)n_keys;
   if (ck < 1 || hw < 1) return 0;
-  return carve_workspace(nullptr, ck, hw).bytes;
+  return carve_workspace(nullptr, ck, hw, tc_group_candidates()).bytes;
 }
 
 // One-time preparation of a workspace: everything zero (published-threshold entries then carry epoch 0, which no
@@ -123,14 +137,16 @@ extern "C" int vosmem_workspace_status(const void *workspace, vosmem_stream_t st
   return VOSMEM_OK;
 }
 
-// run the selection kernel(s) of `n` problems: leaves the per-split candidate lists in each problem's workspace
-static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
+// run the selection kernel(s) of `n` problems: leaves the candidate lists in each problem's workspace and describes
+// them in lists[0..n)
+static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, SplitLists *lists,
                          const PeerThresholds *peers = nullptr) {
+  Workspace ws[MAX_BATCH];
   int path = 0, splits = MAX_SPLITS;
   for (int b = 0; b < n; ++b) {
     int rc = validate_select(d + b);
     if (rc != VOSMEM_OK) return rc;
-    ws[b] = carve_workspace(d[b].workspace, d[b].ck, d[b].hw);
+    ws[b] = carve_workspace(d[b].workspace, d[b].ck, d[b].hw, tc_group_candidates());
     int64_t total = 0;
     for (int s = 0; s < d[b].n_segments; ++s) total += d[b].seg[s].end - d[b].seg[s].begin;
     const int p = resolve_path(d[b]);
@@ -144,8 +160,10 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
     const int sp = choose_splits(p, d[b].hw, total, n);
     splits = sp < splits ? sp : splits;
   }
-  n_lists = splits;                                                          // candidate lists left per query
-  n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : 0;        // published threshold rows (SIMT: none)
+  const bool groups = path == VOSMEM_PATH_TCGEN05 && tc_group_candidates() && !(peers != nullptr && peers->world > 1);
+  const int n_lists = groups ? splits * LISTS_PER_SPLIT : splits;                 // candidate lists left per query
+  const int n_pub = path == VOSMEM_PATH_TCGEN05 ? splits * LISTS_PER_SPLIT : 0;   // published threshold rows (SIMT: none)
+  for (int b = 0; b < n; ++b) lists[b] = split_lists_of(ws[b], n_lists, n_pub, d[b].hw, groups, d + b);
   if (g_stage_events[0]) cudaEventRecord(g_stage_events[0], st);
   int rc;
   if (path != VOSMEM_PATH_TCGEN05) {   // the tcgen05 kernel packs its query tile itself
@@ -155,7 +173,8 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
   if (g_stage_events[1]) cudaEventRecord(g_stage_events[1], st);
   if (peers != nullptr && peers->world > 1)
     VOSMEM_CHECK_ARG(path == VOSMEM_PATH_TCGEN05 && n == 1, "select: thresholds across ranks need the tcgen05 path, one problem");
-  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(d, ws, n, splits, st, peers) : launch_select_simt(*d, ws[0], splits, st);
+  rc = path == VOSMEM_PATH_TCGEN05 ? launch_select_tc(d, ws, n, splits, groups, st, peers)
+                                   : launch_select_simt(*d, ws[0], splits, st);
   if (rc != VOSMEM_OK) return rc;
   if (g_stage_events[2]) cudaEventRecord(g_stage_events[2], st);
   return VOSMEM_OK;
@@ -163,9 +182,8 @@ static int run_selection(const vosmem_select_desc *d, int n, cudaStream_t st, Wo
 
 namespace vosmem {
 // the selection stage alone, for the sharded path (exchange.cu): candidate lists stay in the workspace
-int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
-                           const PeerThresholds *peers) {
-  return run_selection(d, 1, st, ws, n_lists, n_pub, peers);
+int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, SplitLists &lists, const PeerThresholds *peers) {
+  return run_selection(d, 1, st, &lists, peers);
 }
 }  // namespace vosmem
 
@@ -173,17 +191,16 @@ extern "C" int vosmem_select_topk(const vosmem_select_desc *d, float *out_score,
                                   vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(out_score && out_index, "select: null output");
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace ws;
-  int n_lists = 1, n_pub = 1;
-  int rc = run_selection(d, 1, st, &ws, n_lists, n_pub);
+  SplitLists lists;
+  int rc = run_selection(d, 1, st, &lists);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_merge_splits(ws, n_lists, n_pub, d->hw, d->top_k, d->index_base, out_score, out_index, st);
+  rc = launch_merge_splits(lists, d->hw, d->top_k, d->index_base, out_score, out_index, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }
 
 namespace vosmem {
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int n, int n_lists, int n_pub, cudaStream_t st);
+int launch_fused_readout(const vosmem_readout_desc *d, const SplitLists *lists, int n, cudaStream_t st);
 }
 
 // One object group of match_memory: pack -> select -> (merge + softmax + usage + readout in one kernel).
@@ -198,11 +215,10 @@ extern "C" int vosmem_match(const vosmem_select_desc *select, const vosmem_reado
                    readout->hw, readout->top_k);
   VOSMEM_CHECK_ARG(select->index_base == 0, "vosmem_match: index_base must be 0 (use the staged calls for sharded banks)");
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace ws;
-  int n_lists = 1, n_pub = 1;
-  int rc = run_selection(select, 1, st, &ws, n_lists, n_pub);
+  SplitLists lists;
+  int rc = run_selection(select, 1, st, &lists);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_fused_readout(readout, &ws, 1, n_lists, n_pub, st);
+  rc = launch_fused_readout(readout, &lists, 1, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }
@@ -219,11 +235,10 @@ extern "C" int vosmem_match_batch(const vosmem_select_desc *select, const vosmem
     VOSMEM_CHECK_ARG(select[b].index_base == 0, "vosmem_match_batch: index_base must be 0");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace ws[MAX_BATCH];
-  int n_lists = 1, n_pub = 1;
-  int rc = run_selection(select, n, st, ws, n_lists, n_pub);
+  SplitLists lists[MAX_BATCH];
+  int rc = run_selection(select, n, st, lists);
   if (rc != VOSMEM_OK) return rc;
-  rc = launch_fused_readout(readout, ws, n, n_lists, n_pub, st);
+  rc = launch_fused_readout(readout, lists, n, st);
   if (g_stage_events[3]) cudaEventRecord(g_stage_events[3], st);
   return rc;
 }

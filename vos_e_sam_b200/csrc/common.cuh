@@ -19,6 +19,13 @@ constexpr int CAND_SLOTS = 120;                 // per (split, query) candidate 
 constexpr int MAX_SPLITS = 32;
 constexpr int MAX_BATCH = VOSMEM_MAX_BATCH;      // independent problems (sequences) one launch can carry (blockIdx.z)
 constexpr int LISTS_PER_SPLIT = 2;              // the tcgen05 kernel publishes two thresholds per (split, query)
+// Group candidates (select_tc.cu, GROUPS mode): a candidate is a group of 8 consecutive keys of the packed image,
+// scored by the maximum of its 8 similarities; all 8 are kept next to the entry so that the consumer can expand the
+// best 32 groups of a query into its best k keys without touching the keys again (merge.cuh, expand_groups).
+constexpr int GROUP_KEYS = 8;
+constexpr int GSLOTS = 60;                      // group entries per (virtual split, query)
+static_assert(LISTS_PER_SPLIT * GSLOTS == CAND_SLOTS, "group lists reuse the exchange rows of the element lists");
+#define VOSMEM_GROUP_LOG 192                    // records of the per-list score log of the selection kernel (two halves)
 
 void set_error(const char *fmt, ...);
 #define VOSMEM_CHECK_ARG(cond, ...)              \
@@ -139,6 +146,10 @@ struct CandEntry {   // one exchanged candidate: score + index on the candidate 
   int index;
 };
 static_assert(sizeof(CandEntry) == 8, "exchange entries are read / written as 8-byte words");
+// Group mode: a list entry is CandEntry{maximum of the group's 8 scores, locator} with locator bit 31 = segment,
+// bits 0-30 = group index inside the bank (first key / 8); the 8 scores (-inf for keys outside the segment's candidate
+// range) sit at the same (list, query, slot) position of a parallel array of 32-byte records.
+constexpr uint32_t GROUP_SEG_BIT = 0x80000000u;
 
 // A published threshold (select_tc.cu, "Thresholds") is only meaningful for the launch that wrote it: the entry
 // carries that launch's epoch and reads of any other epoch see -inf, so the workspace needs no reset between
@@ -174,7 +185,11 @@ struct Workspace {
   PubEntry *pub;               // pub_rows * hw_pad: lower bound published per (virtual split, query) by the current launch
   PubEntry *pub2;              // the same for the (smaller) rank used when thresholds are shared across ranks
   CandEntry *cand;             // splits * hw_pad * CAND_SLOTS
-  int *cand_count;             // splits * hw_pad
+  int *cand_count;             // splits * LISTS_PER_SPLIT * hw_pad
+  float *glog;                 // splits * LISTS_PER_SPLIT * hw_pad * VOSMEM_GROUP_LOG x 8 scores: the selection kernel's
+                               // per-list score logs (scratch of that kernel only)
+  float *gscore;               // splits * LISTS_PER_SPLIT * hw_pad * GSLOTS x 8 scores (tcgen05 kernel, group mode; the
+                               // entries themselves then use `cand` as [virtual split][hw_pad][GSLOTS])
   int pub_rows;                // rows of `pub` (= splits_cap * LISTS_PER_SPLIT)
   float *qvec;                 // SIMT path: (2*ck + 1) x hw_pad, c-major  [-e | 2*q*e | -sum e q^2]
   int64_t bytes;
@@ -190,7 +205,8 @@ inline int splits_cap(int hw) {
   return (int)s;
 }
 
-inline Workspace carve_workspace(void *base, int ck, int hw) {
+// groups: room for the group-candidate mode of the tcgen05 selection (score logs + exchanged scores; ~140 KB per query)
+inline Workspace carve_workspace(void *base, int ck, int hw, bool groups) {
   Workspace w;
   const int64_t cap = (int64_t)splits_cap(hw) * LISTS_PER_SPLIT;   // candidate lists per query
   int64_t n_qtiles = ceil_div64(hw, TQ);
@@ -209,6 +225,8 @@ inline Workspace carve_workspace(void *base, int ck, int hw) {
   w.pub_rows = (int)cap;
   w.cand = reinterpret_cast<CandEntry *>(take((int64_t)splits_cap(hw) * hw_pad * CAND_SLOTS * 8));
   w.cand_count = reinterpret_cast<int *>(take(cap * hw_pad * 4));
+  w.gscore = reinterpret_cast<float *>(take(groups ? cap * hw_pad * GSLOTS * GROUP_KEYS * 4 : 0));
+  w.glog = reinterpret_cast<float *>(take(groups ? cap * hw_pad * VOSMEM_GROUP_LOG * GROUP_KEYS * 4 : 0));
   w.qvec = reinterpret_cast<float *>(take((int64_t)hw_pad * (2 * ck + 1) * 4));
   w.bytes = off;
   return w;
@@ -230,9 +248,10 @@ struct PeerThresholds {
   int world = 1, rank = 0;
   PubEntry *rank_pub[VOSMEM_MAX_RANKS] = {};
 };
-int launch_select_tc(const vosmem_select_desc *d, const Workspace *ws, int n, int splits, cudaStream_t st,
+int launch_select_tc(const vosmem_select_desc *d, const Workspace *ws, int n, int splits, bool groups, cudaStream_t st,
                      const PeerThresholds *peers = nullptr);
-int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
+struct SplitLists;
+int launch_merge_splits(const SplitLists &lists, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st);
 int choose_splits(int path, int hw, int64_t n_total, int batch = 1);
 

@@ -19,7 +19,7 @@ constexpr int EXCH_K = VOSMEM_EXCH_K;
 struct PushArgs {
   SplitLists lists;
   int hw, top_k, per, world, rank;
-  int64_t index_base;
+  int64_t index_base, index_base1, seg0_len;
   uint2 *dst[VOSMEM_MAX_RANKS];
   uint32_t *flag[VOSMEM_MAX_RANKS];
   uint32_t seq;
@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(256, MB <= 4 ? 4 : 2) merge_push_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   if (q < a.hw) {
-    const WarpTop32 top = merge_query<MB>(a.lists, q, buf_s[warp], buf_i[warp], lane);
+    const WarpTop32 top = merge_lists_of_query<MB>(a.lists, q, a.top_k, buf_s[warp], buf_i[warp], lane);
     const bool have = lane < a.top_k && top.i != 0x7fffffff;
     const int owner = q / a.per, local = q - owner * a.per;
-    const uint2 entry = make_uint2(__float_as_uint(have ? top.s : -INFINITY), have ? (uint32_t)(top.i + (int)a.index_base) : 0xffffffffu);
+    const int global = top.i < a.seg0_len ? top.i + (int)a.index_base : top.i - (int)a.seg0_len + (int)a.index_base1;
+    const uint2 entry = make_uint2(__float_as_uint(have ? top.s : -INFINITY), have ? (uint32_t)global : 0xffffffffu);
     a.dst[owner][(int64_t)local * EXCH_K + lane] = entry;   // 256 contiguous bytes per query
   }
   signal_when_grid_done(a.ticket, a.flag, a.world, a.seq);
@@ -113,8 +114,7 @@ __global__ void wait_flags_kernel(const uint32_t *flags, uint32_t mask, uint32_t
 
 }  // namespace
 
-int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, Workspace *ws, int &n_lists, int &n_pub,
-                           const PeerThresholds *peers);
+int run_selection_for_push(const vosmem_select_desc *d, cudaStream_t st, SplitLists &lists, const PeerThresholds *peers);
 
 }  // namespace vosmem
 
@@ -131,8 +131,6 @@ extern "C" int vosmem_select_push(const vosmem_select_desc *select, const vosmem
   for (int r = 0; r * (int64_t)push->per < select->hw; ++r)
     VOSMEM_CHECK_ARG(push->dst[r] != nullptr, "vosmem_select_push: no destination for owner rank %d", r);
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace ws;
-  int n_lists = 1, n_pub = 1;
   PeerThresholds peers;
   peers.world = push->world;
   peers.rank = push->rank;
@@ -141,16 +139,22 @@ extern "C" int vosmem_select_push(const vosmem_select_desc *select, const vosmem
     peers.rank_pub[r] = static_cast<PubEntry *>(push->rank_pub[r]);
     shared = shared && push->rank_pub[r] != nullptr;
   }
-  int rc = run_selection_for_push(select, st, &ws, n_lists, n_pub, shared ? &peers : nullptr);
-  if (rc != VOSMEM_OK) return rc;
   PushArgs a{};
-  a.lists = SplitLists{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, (int)round_up64(select->hw, TQ), ws.ctl};
+  int64_t n_keys = 0;
+  for (int s = 0; s < select->n_segments && s < VOSMEM_MAX_SEGMENTS; ++s) n_keys += select->seg[s].end - select->seg[s].begin;
+  if (n_keys > 0) {
+    int rc = run_selection_for_push(select, st, a.lists, shared ? &peers : nullptr);
+    if (rc != VOSMEM_OK) return rc;
+  }   // else: no lists (splits == 0) -> every query's exchange list is pushed empty, the flags are raised as usual
+  const int n_lists = a.lists.splits;
   a.hw = select->hw;
   a.top_k = select->top_k;
   a.per = push->per;
   a.world = push->world;
   a.rank = push->rank;
   a.index_base = push->index_base;
+  a.seg0_len = push->seg0_len < 0 ? ((int64_t)1 << 40) : push->seg0_len;
+  a.index_base1 = push->index_base1;
   for (int r = 0; r < push->world; ++r) {
     a.dst[r] = static_cast<uint2 *>(push->dst[r]);
     a.flag[r] = push->flag[r];

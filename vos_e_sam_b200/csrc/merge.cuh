@@ -8,12 +8,37 @@ constexpr int MERGE_MAX_SPLITS = 16;
 constexpr int MERGE_BUF = 128;
 
 struct SplitLists {
-  const CandEntry *cand;    // [splits][hw_pad][CAND_SLOTS]
+  const CandEntry *cand;    // [splits][hw_pad][slots]
   const int *cand_count;    // [splits][hw_pad]
   const PubEntry *pub;      // [pub_rows][hw_pad] published lower bounds per (virtual split, query) of the selection launch
   int splits, pub_rows, hw_pad;   // pub_rows == 0: the selection published nothing (SIMT path), no threshold
   const WsControl *ctl;     // ctl->last = the epoch the selection launch that filled the lists ran under
+  // Group mode (tcgen05 selection, select_tc.cu): gscore != NULL, `splits` counts the VIRTUAL splits, a list has
+  // GSLOTS entries {group maximum, locator} and gscore holds the 8 scores of every entry.  merge_query then returns
+  // the best 32 GROUPS (index = list << 6 | slot) and expand_groups turns them into the best 32 keys.
+  const float *gscore;
+  int seg_begin[2], len0;   // candidate index of key n of segment s = n - seg_begin[s] + (s ? len0 : 0)
 };
+
+// host side: the lists a selection launch left in its workspace
+inline SplitLists split_lists_of(const Workspace &ws, int n_lists, int n_pub, int hw, bool groups,
+                                 const vosmem_select_desc *d) {
+  SplitLists L{};
+  L.cand = ws.cand;
+  L.cand_count = ws.cand_count;
+  L.pub = ws.pub;
+  L.splits = n_lists;
+  L.pub_rows = n_pub;
+  L.hw_pad = (int)round_up64(hw, TQ);
+  L.ctl = ws.ctl;
+  L.gscore = groups ? ws.gscore : nullptr;
+  if (groups && d != nullptr) {
+    L.seg_begin[0] = (int)d->seg[0].begin;
+    L.seg_begin[1] = d->n_segments > 1 ? (int)d->seg[1].begin : 0;
+    L.len0 = (int)(d->seg[0].end - d->seg[0].begin);
+  }
+  return L;
+}
 
 // Folds `buffered` parked candidates into the running best 32.  Out of line and by value: the sorting network is
 // long, and merge_query has many call sites for it (instruction-cache footprint of the readout kernel).
@@ -33,8 +58,11 @@ static __device__ __noinline__ WarpTop32 drain_buffer(WarpTop32 top, const float
 // before the sorting network sees them, which usually leaves 32-64 survivors.  buf_s / buf_i: MERGE_BUF entries of
 // warp-private shared memory.
 // MB: lists whose first 32 slots are loaded together (registers: 2 * MB per lane).
-template <int MB = MERGE_MAX_SPLITS>
+// GR: group mode (entries per row and the index payload differ; a compile-time switch so that the single-key path
+// keeps its constant row stride).
+template <int MB = MERGE_MAX_SPLITS, bool GR = false>
 __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, float *buf_s, int *buf_i, int lane) {
+  constexpr int SLOTS = GR ? GSLOTS : CAND_SLOTS;
   WarpTop32 top;
   top.init();
   int buffered = 0;
@@ -53,8 +81,9 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
 #pragma unroll
     for (int y = 0; y < MB; ++y) {
       if (y0 + y < L.splits) {
-        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
+        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * SLOTS;
         c[y] = L.cand[row + lane];
+        if (GR) c[y].index = ((y0 + y) << 6) | lane;   // group mode: where the group's record sits
       }
     }
     if (!tau_ready) {  // lane y owns list y
@@ -116,14 +145,79 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
       const int cnt = __shfl_sync(FULL, my_cnt, y);
       offer(c[y].score >= cut && c[y].score != -INFINITY, c[y].score, c[y].index);
       for (int off = 32; off < cnt; off += 32) {   // rare: a list longer than 32 entries
-        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * CAND_SLOTS;
-        const CandEntry c2 = L.cand[row + off + lane];
+        const int64_t row = ((int64_t)(y0 + y) * L.hw_pad + q) * SLOTS;
+        CandEntry c2 = L.cand[row + (off + lane < SLOTS ? off + lane : 0)];
+        if (GR) c2.index = ((y0 + y) << 6) | (off + lane);
         offer(off + lane < cnt && c2.score >= cut && c2.index != 0x7fffffff, c2.score, c2.index);
       }
     }
   }
   drain();
   return top;
+}
+
+// Group mode: lane l holds the l-th best GROUP of query q (top.s = its maximum, top.i = list << 6 | slot, or
+// 0x7fffffff for none).  The best k keys of the query all sit in its best k groups (a key's group scores at least the
+// key), so: read the 8 scores of the lane's group, take the exact best 32 of the 32 group maxima plus every other
+// score that reaches the k-th best maximum (a lower bound of the k-th best key).  Returns keys: (score, candidate index).
+// (out of line and by value, like drain_buffer: keeps the register budget of the readout kernel's gather loop intact)
+static __device__ __noinline__ WarpTop32 expand_groups(const SplitLists L, int q, const WarpTop32 g, int top_k, int lane) {
+  float sc[GROUP_KEYS];
+  int idx0 = 0;
+  const bool have = g.i != 0x7fffffff;
+  if (have) {
+    const int y = g.i >> 6, slot = g.i & 63;
+    const int64_t at = ((int64_t)y * L.hw_pad + q) * GSLOTS + slot;
+    const uint32_t loc = (uint32_t)__ldcg(&L.cand[at].index);
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(L.gscore + at * GROUP_KEYS));
+    const float4 b = __ldcg(reinterpret_cast<const float4 *>(L.gscore + at * GROUP_KEYS) + 1);
+    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w;
+    sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+    const int s = loc >> 31;
+    idx0 = (int)((loc & ~GROUP_SEG_BIT) * GROUP_KEYS) - L.seg_begin[s] + (s ? L.len0 : 0);
+  } else {
+#pragma unroll
+    for (int j = 0; j < GROUP_KEYS; ++j) sc[j] = -INFINITY;
+  }
+  // the lane's best key first
+  float m1 = sc[0];
+  int j1 = 0;
+#pragma unroll
+  for (int j = 1; j < GROUP_KEYS; ++j)
+    if (sc[j] > m1) { m1 = sc[j]; j1 = j; }
+  WarpTop32 top;
+  top.init();
+  top.push(m1, m1 > -INFINITY ? idx0 + j1 : 0x7fffffff, lane);
+  const float floor_k = __shfl_sync(FULL, top.s, top_k - 1);
+  bool more = false;
+#pragma unroll
+  for (int j = 0; j < GROUP_KEYS; ++j) more = more || (j != j1 && sc[j] >= floor_k && sc[j] > -INFINITY);
+  if (__any_sync(FULL, more)) {
+#pragma unroll 1
+    for (int j = 0; j < GROUP_KEYS; ++j) {
+      float v = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < GROUP_KEYS; ++u) v = (u == j) ? sc[u] : v;   // (no dynamic register indexing)
+      const bool ok = j != j1 && v >= floor_k && v > -INFINITY;
+      if (__any_sync(FULL, ok)) top.push(ok ? v : -INFINITY, ok ? idx0 + j : 0x7fffffff, lane);
+    }
+  }
+  return top;
+}
+
+// group mode, out of line: the single-key path of the callers keeps the registers and code layout it had without it
+template <int MB>
+static __device__ __noinline__ WarpTop32 merge_groups_of_query(const SplitLists L, int q, int top_k, float *buf_s, int *buf_i,
+                                                               int lane) {
+  return expand_groups(L, q, merge_query<MB, true>(L, q, buf_s, buf_i, lane), top_k, lane);
+}
+
+// merge + (group mode) expansion: what every consumer of the selection's lists calls
+template <int MB = MERGE_MAX_SPLITS>
+__device__ __forceinline__ WarpTop32 merge_lists_of_query(const SplitLists &L, int q, int top_k, float *buf_s, int *buf_i,
+                                                          int lane) {
+  if (L.gscore == nullptr) return merge_query<MB, false>(L, q, buf_s, buf_i, lane);
+  return merge_groups_of_query<MB>(L, q, top_k, buf_s, buf_i, lane);
 }
 
 }  // namespace vosmem

@@ -14,6 +14,8 @@
 //              warp per query, which removes a kernel and a round trip from vosmem_match;
 //   exchange : N-sharded bank -- the kernel waits for the flags of the source ranks, then merges the `world`
 //              exchange lists that the ranks pushed into this rank's memory for its own query slice.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "merge.cuh"
 
@@ -121,7 +123,7 @@ __device__ __forceinline__ void resolve_query(const ReadoutArgs &a, int q, bool 
   int64_t gi = -1;
   if (q < a.hw) {
     if (FRONT == FRONT_FUSED) {
-      const WarpTop32 top = merge_query<12>(a.lists, q, m_s, m_i, lane);
+      const WarpTop32 top = merge_lists_of_query<12>(a.lists, q, a.top_k, m_s, m_i, lane);
       if (lane < a.top_k && top.i != 0x7fffffff) { s = top.s; gi = top.i; }
     } else if (FRONT == FRONT_EXCHANGE) {
       // one entry per lane from every source rank's list, eight lists in flight at a time, folded into the best 32
@@ -307,10 +309,18 @@ int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStrea
   for (int i = 0; i < n; ++i) grouped = grouped || b.p[i].out_group_rows != 0;
   for (int i = 0; i < n; ++i)
     VOSMEM_CHECK_ARG(!grouped || b.p[i].out_group_rows != 0, "readout: grouped and plain output rows in one batch");
+  static const int carveout = [] { const char *e = getenv("VOSMEM_RD_CARVEOUT"); return e ? atoi(e) : -1; }();   // experiment
+#define VOSMEM_LAUNCH_RD_AS(T, VEC, GR)                                                                           \
+  do {                                                                                                            \
+    if (carveout >= 0)                                                                                            \
+      VOSMEM_CUDA(cudaFuncSetAttribute(softmax_readout_kernel<T, VEC, RQ, FRONT, GR>,                             \
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, carveout));                \
+    softmax_readout_kernel<T, VEC, RQ, FRONT, GR><<<grid, RTHREADS, 0, st>>>(b);                                  \
+  } while (0)
 #define VOSMEM_LAUNCH_RD(T, VEC)                                                                    \
   do {                                                                                              \
-    if (grouped) softmax_readout_kernel<T, VEC, RQ, FRONT, true><<<grid, RTHREADS, 0, st>>>(b);     \
-    else softmax_readout_kernel<T, VEC, RQ, FRONT, false><<<grid, RTHREADS, 0, st>>>(b);            \
+    if (grouped) VOSMEM_LAUNCH_RD_AS(T, VEC, true);                                                 \
+    else VOSMEM_LAUNCH_RD_AS(T, VEC, false);                                                        \
   } while (0)
   if (value_dtype == VOSMEM_F32) {
     if (vec_ok) VOSMEM_LAUNCH_RD(float, 4);
@@ -320,6 +330,7 @@ int launch(const ReadoutBatch &b, int n, int value_dtype, bool vec_ok, cudaStrea
     else VOSMEM_LAUNCH_RD(__nv_bfloat16, 1);
   }
 #undef VOSMEM_LAUNCH_RD
+#undef VOSMEM_LAUNCH_RD_AS
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
@@ -362,7 +373,7 @@ int fill_args(const vosmem_readout_desc *d, ReadoutArgs &a, bool &vec_ok) {
 }  // namespace
 
 // fused front end, used by vosmem_match / vosmem_match_batch after the selection kernel
-int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int n, int n_lists, int n_pub, cudaStream_t st) {
+int launch_fused_readout(const vosmem_readout_desc *d, const SplitLists *lists, int n, cudaStream_t st) {
   VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "readout: batch of %d problems outside [1, %d]", n, MAX_BATCH);
   ReadoutBatch b{};
   bool vec_all = true;
@@ -372,7 +383,7 @@ int launch_fused_readout(const vosmem_readout_desc *d, const Workspace *ws, int 
     if (rc != VOSMEM_OK) return rc;
     VOSMEM_CHECK_ARG(d[i].value_dtype == d[0].value_dtype, "readout: problems of one batch must share the value storage type");
     vec_all = vec_all && vec_ok;
-    b.p[i].lists = SplitLists{ws[i].cand, ws[i].cand_count, ws[i].pub, n_lists, n_pub, (int)round_up64(d[i].hw, TQ), ws[i].ctl};
+    b.p[i].lists = lists[i];
   }
   return launch<4, FRONT_FUSED>(b, n, d[0].value_dtype, vec_all, st);
 }

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256, MB <= 4 ? 4 : 2) merge_splits_kernel(Spli
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   if (q >= hw) return;
-  const WarpTop32 top = merge_query<MB>(L, q, buf_s[warp], buf_i[warp], lane);
+  const WarpTop32 top = merge_lists_of_query<MB>(L, q, top_k, buf_s[warp], buf_i[warp], lane);
   if (lane < top_k) {
     const bool have = top.i != 0x7fffffff;
     out_score[(int64_t)q * top_k + lane] = have ? top.s : -INFINITY;
@@ -162,11 +162,9 @@ int launch_select_simt(const vosmem_select_desc &d, const Workspace &ws, int spl
   return VOSMEM_OK;
 }
 
-int launch_merge_splits(const Workspace &ws, int n_lists, int n_pub, int hw, int top_k, int64_t index_base, float *out_score,
+int launch_merge_splits(const SplitLists &L, int hw, int top_k, int64_t index_base, float *out_score,
                         int64_t *out_index, cudaStream_t st) {
-  int hw_pad = (int)round_up64(hw, TQ);
-  SplitLists L{ws.cand, ws.cand_count, ws.pub, n_lists, n_pub, hw_pad, ws.ctl};
-  if (n_lists <= 4) merge_splits_kernel<4><<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
+  if (L.splits <= 4) merge_splits_kernel<4><<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
   else merge_splits_kernel<MERGE_MAX_SPLITS><<<(hw + 7) / 8, 256, 0, st>>>(L, hw, top_k, index_base, out_score, out_index);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;

@@ -24,6 +24,17 @@
 //                      lists to their best 32 with a bitonic network over packed 32-bit keys.
 // Each CTA leaves <= 120 candidates per query in the exchange buffer; the merge (merge.cuh) finishes.
 //
+// GROUPS mode (opt-in: VOSMEM_TC_CANDIDATES=groups, see api.cu; measured against single keys in DESIGN.md 3.1).  Appending single scores costs the epilogue ~6.5 instructions per score of
+// every 8-column group in which ANY lane of the warp has a survivor -- with ~1 survivor per query row and tile (short
+// key streams: DAVIS, a rank's shard of a long bank) that is every group, and the epilogue, not the tensor pipe, sets
+// the pace (~1 400 against 800 cycles per tile).  In GROUPS mode the candidates are the 8-column groups themselves,
+// scored by their maximum: one compare and one predicated append per group -- the entry {maximum, position} into the
+// shared-memory list, the group's 8 scores into a per-list log in global memory (see "GROUPS mode" below).
+// Everything said about thresholds below holds with "group" for "key": the best 32 keys of a query lie in its best 32
+// groups, a group maximum is the score of a real key, and maxima of distinct groups are scores of distinct keys.
+// The consumer (merge.cuh) merges the lists into the best 32 groups and expands them into the best k keys from the
+// 8 recorded scores -- the keys are never read again.
+//
 // Thresholds.  A query's threshold is only ever a LOWER bound of its true 32nd-best score, so no true
 // top-k (k <= 32) member is dropped:
 //   local : after a cooperative cut, the (truncated) 32nd-best score of this warp's own candidates;
@@ -48,6 +59,7 @@
 // Rows carry the launch epoch, which all ranks advance in step (same call sequence on the engine's workspaces); a
 // row that is missing or stale reads as -inf, i.e. no cross-rank bound yet.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -112,6 +124,9 @@ struct TcArgs {
   WsControl *ctl;         // device-side launch epoch (tags this launch's published values), departure counter, error flags
   CandEntry *cand;
   int *cand_count;
+  float *gscore;       // GROUPS mode: 8 scores per entry of `cand` (then laid out [virtual split][hw_pad][GSLOTS])
+  float *glog;         // GROUPS mode: score logs, VOSMEM_GROUP_LOG records of 8 scores per (virtual split, query)
+  int exp;             // experiment switches (VOSMEM_TC_EXP; 0 in production)
   long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
 };
 
@@ -285,6 +300,77 @@ __device__ __noinline__ ListState relieve_lists(ListState st, Entry *cs, const v
   return st;
 }
 
+// ---- GROUPS mode ---------------------------------------------------------------------------------------------------
+// The list entries {group maximum, log position << 20 | group index in the CTA's stream} live in the same shared-memory
+// lists as the single-key entries (compact_list / relieve_lists treat the index as an opaque payload); the groups' 8
+// scores go to a per-list LOG in global memory: one full 32-byte sector per append (a partial-sector store would make
+// L2 fetch the rest of the sector first -- measured: three 8 / 16-byte stores per append cost ~160 cycles), written at a
+// position that only ever advances, so records never move when the list is compacted or cut.  The log has two halves
+// of LOG_HALF records; when the active half is full the (<= CSLOTS) live records are copied to the other half
+// (flip_log: rare -- a list sees ~10 appends at the DAVIS shape, ~80 over a 100 000-key stream).
+constexpr int LOG_HALF = VOSMEM_GROUP_LOG / 2;
+constexpr uint32_t GIDX_BITS = 20, GIDX_MASK = (1u << GIDX_BITS) - 1;   // group index in the CTA's stream: 8 x tile + group
+static_assert(LOG_HALF >= CSLOTS + TK / 8, "a flipped log must have room for one more tile");
+
+struct Rec8 { uint32_t w[8]; };
+__device__ __forceinline__ Rec8 ldg_rec(const float *p) {
+  Rec8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_rec(float *p, const Rec8 &r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]),
+               "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]) : "memory");
+}
+// if (gmax >= thr) { list[off] = {gmax, lp << 20 | gidx}; log[lp] = 8 scores; off += stride; ++lp }   -- predicated
+#define VOSMEM_APPEND_GROUP(off, lp, logp, thr, gmax, gidx, v, j0)                                                   \
+  asm volatile(                                                                                                     \
+      "{\n\t.reg .pred p;\n\t.reg .b64 ar;\n\t.reg .b32 ix;\n\t"                                                \
+      "setp.ge.f32 p, %3, %4;\n\t"                                                                                  \
+      "mad.wide.u32 ar, %1, 32, %2;\n\t"                                                                            \
+      "shl.b32 ix, %1, 20;\n\t"                                                                                     \
+      "or.b32 ix, ix, %5;\n\t"                                                                                      \
+      "@p st.shared.v2.b32 [%0], {%6, ix};\n\t"                                                                     \
+      "@p st.global.v8.b32 [ar], {%7, %8, %9, %10, %11, %12, %13, %14};\n\t"                                        \
+      "@p add.u32 %0, %0, %15;\n\t"                                                                                 \
+      "@p add.u32 %1, %1, 1;\n\t}"                                                                                  \
+      : "+r"(off), "+r"(lp)                                                                                         \
+      : "l"(logp), "f"(gmax), "f"(thr), "r"(gidx), "r"(__float_as_uint(gmax)), "r"((v)[(j0)]), "r"((v)[(j0) + 1]),   \
+        "r"((v)[(j0) + 2]), "r"((v)[(j0) + 3]), "r"((v)[(j0) + 4]), "r"((v)[(j0) + 5]), "r"((v)[(j0) + 6]),           \
+        "r"((v)[(j0) + 7]), "n"(CS_E * 8)                                                                            \
+      : "memory")
+
+// The active half of this thread's log is (nearly) full: copy the records its list still refers to into the other half,
+// in list order, and re-point the entries.  Thread-private (every lane of the warp runs it; lanes with short lists
+// just move few records).  Returns the new log position.
+// (inlined: cicc 12.9 crashes on this function when it is kept out of line)
+__device__ __forceinline__ uint32_t flip_log(ListState st, float *logp, uint32_t lp) {
+  const uint32_t other = lp >= (uint32_t)LOG_HALF ? 0u : (uint32_t)LOG_HALF;   // first record of the other half
+  const int n = (int)((st.off - st.base) / SS);
+  const int nmax = __reduce_max_sync(FULL, n);
+  for (int e0 = 0; e0 < nmax; e0 += 4) {
+    Rec8 r[4];
+    uint32_t ix[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool in = e0 + u < n;
+      ix[u] = in ? lds_entry(st.base + (e0 + u) * SS).index : 0u;
+      r[u] = ldg_rec(logp + (size_t)(ix[u] >> GIDX_BITS) * GROUP_KEYS);   // (lanes past their list read record 0)
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (e0 + u < n) {
+        stg_rec(logp + (size_t)(other + e0 + u) * GROUP_KEYS, r[u]);
+        const uint32_t addr = st.base + (e0 + u) * SS + 4, val = ((other + e0 + u) << GIDX_BITS) | (ix[u] & GIDX_MASK);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+      }
+    }
+  }
+  return other + n;
+}
+
 // One pass of the refresher warp over the published rows: NB x 4 independent 8-byte loads in flight per lane.  Rows
 // past the end re-read the last row (harmless for a minimum), so there is no branch between the loads and they are
 // all issued before the first use.
@@ -376,7 +462,8 @@ __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsi
 // R = tracked / published rank per virtual split (see "Thresholds"); SHARED = thresholds across ranks (a separate
 // instantiation: the extra uniform state of that path costs the MMA warp its register -> uniform-register-free issue
 // loop, 39.4 against 37.4 us at the DAVIS shape, so single-GPU launches do not carry it)
-template <int R, bool SHARED>
+// GROUPS = candidates are 8-column groups appended to global lists (header comment)
+template <int R, bool SHARED, bool GROUPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_constant__ TcBatch batch) {
   const TcArgs &a = batch.p[blockIdx.z];
   extern __shared__ __align__(128) unsigned char smem[];
@@ -565,6 +652,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     ListState st;
     st.base = ptx::smem_u32(cs) + row * 8;
     st.off = st.base;
+    // GROUPS mode: this thread's score log and its next free record (see flip_log)
+    float *const logp = a.glog + ((int64_t)vsplit * a.hw_pad + qtile * TQ + row) * (VOSMEM_GROUP_LOG * GROUP_KEYS);
+    uint32_t lp = 0;
+    int log_bound = 0;   // warp-uniform upper bound of the records any lane holds in the active half of its log
     // Candidates are kept when score >= threshold: the shared threshold is the score of a real key, and with exact
     // ties at it (duplicated memory frames, uniform regions) a strict compare would drop keys the reference's
     // torch.topk returns.  The initial threshold is the lowest FINITE float, not -inf, so that masked columns
@@ -579,7 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     PubEntry *pub_mine = a.pub + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
     PubEntry *pub2_mine = a.pub2 + (int64_t)vsplit * a.hw_pad + qtile * TQ + quarter * 32;
     float pub2 = -INFINITY;   // what this thread has published for the cross-rank bound
-    long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0;
+    long long t_wait = 0, t_relieve = 0, t_first = 0, t_ld = 0, t_max = 0, t_app = 0, t_x0 = 0, t_x1 = 0;
     int n_active = 0, n_relieve = 0;
     int len_bound = 0;   // warp-uniform upper bound of the longest list of this warp
     // Tiles are handed out dynamically to the two warps of a lane quarter (shared-memory counter), so a warp that is
@@ -592,6 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     // tiles that may hold columns outside the candidate range (first / last tile of a segment), as stream positions
     const int edge0 = -(int)g_lo, edge1 = (int)(a.seg[0].tiles - 1 - g_lo), edge2 = edge1 + 1,
               edge3 = (int)(a.tiles_total - 1 - g_lo);
+    const int64_t g_tiles0 = a.seg[0].tiles, g_tile0 = a.seg[0].tile0, g_tile1 = a.seg[1].tile0;   // (GROUPS: locators)
     const long long t_begin = TICK();
     for (int i = __shfl_sync(FULL, grabbed, 0); i < n_tiles; i = __shfl_sync(FULL, grabbed, 0), ++n_done) {
       const int buf = i % ACC_BUFS;
@@ -697,31 +789,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       const long long tp2 = TICK();
       t_max += tp2 - tp1;
 
-      const uint32_t li0 = (uint32_t)i * TK;
-#pragma unroll
-      for (int g8 = 0; g8 < TK / 8; ++g8) {
-        if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
-          ++n_active;
-          // slot addresses first (one select + add per column, each in a fresh register), then the predicated
-          // stores: no store waits for the previous store to release its address register
-          uint32_t slot[9];
-          slot[0] = st.off;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) >= st.tau ? SS : 0u);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int j = g8 * 8 + jj;
-            if (__uint_as_float(v[j]) >= st.tau)
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot[jj]), "r"(v[j]), "r"(li0 + j) : "memory");
-          }
-          st.off = slot[8];
-          // Lists that could overflow during the next 8 columns.  The warp-uniform bound makes the real (voted) check
-          // rare: lists are short once the shared thresholds work.
-          len_bound += 8;
-          if (len_bound > PRUNE_ABOVE) {
+      if constexpr (GROUPS) {
+        if (active) {   // warp-uniform
+          // at most 8 appends per list and tile: make room first if some list (or the active half of some log) could
+          // overflow.  The warp-uniform bounds make the real (voted) checks rare.
+          if (len_bound + TK / 8 > CSLOTS) {
             len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
-            if (len_bound > PRUNE_ABOVE) {
+            if (len_bound + TK / 8 > CSLOTS) {
               const long long tr0 = TICK();
               const float pub_before = st.pub;
               st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
@@ -729,6 +803,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
               t_relieve += TICK() - tr0;
               ++n_relieve;
               len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+            }
+          }
+          if (log_bound + TK / 8 > LOG_HALF) {
+            log_bound = __reduce_max_sync(FULL, (int)(lp >= (uint32_t)LOG_HALF ? lp - LOG_HALF : lp));
+            if (log_bound + TK / 8 > LOG_HALF) {
+              lp = flip_log(st, logp, lp);
+              log_bound = len_bound;   // a flipped half holds exactly the list's records
+            }
+          }
+          const uint32_t gi0 = (uint32_t)i * (TK / 8);   // group index in this CTA's stream
+          const float thr = (a.exp & 1) ? INFINITY : st.tau;   // experiment: nothing is appended
+          const long long tx1 = TICK();
+#pragma unroll
+          for (int g8 = 0; g8 < TK / 8; ++g8) {
+            if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
+              ++n_active;
+              VOSMEM_APPEND_GROUP(st.off, lp, logp, thr, gm[g8], gi0 + g8, v, g8 * 8);
+            }
+          }
+          t_x1 += TICK() - tx1;
+          const int added = __popc(active);
+          len_bound += added;
+          log_bound += added;
+        }
+      } else {
+        const uint32_t li0 = (uint32_t)i * TK;
+#pragma unroll
+        for (int g8 = 0; g8 < TK / 8; ++g8) {
+          if (active & (1u << g8)) {   // warp-uniform; in steady state most groups are skipped
+            ++n_active;
+            // slot addresses first (one select + add per column, each in a fresh register), then the predicated
+            // stores: no store waits for the previous store to release its address register
+            uint32_t slot[9];
+            slot[0] = st.off;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              slot[jj + 1] = slot[jj] + (__uint_as_float(v[g8 * 8 + jj]) >= st.tau ? SS : 0u);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = g8 * 8 + jj;
+              if (__uint_as_float(v[j]) >= st.tau)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot[jj]), "r"(v[j]), "r"(li0 + j) : "memory");
+            }
+            st.off = slot[8];
+            // Lists that could overflow during the next 8 columns.  The warp-uniform bound makes the real (voted) check
+            // rare: lists are short once the shared thresholds work.
+            len_bound += 8;
+            if (len_bound > PRUNE_ABOVE) {
+              len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+              if (len_bound > PRUNE_ABOVE) {
+                const long long tr0 = TICK();
+                const float pub_before = st.pub;
+                st = relieve_lists(st, cs, tau_sh + row, quarter, lane, R);
+                if (st.pub > pub_before) pub_store(pub_mine + lane, st.pub, epoch);
+                t_relieve += TICK() - tr0;
+                ++n_relieve;
+                len_bound = __reduce_max_sync(FULL, (int)((st.off - st.base) / SS));
+              }
             }
           }
         }
@@ -739,6 +871,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
     if (lane == 0) atomicAdd(const_cast<uint32_t *>(epi_done), 1u);   // lets the refresher warp retire
     const long long t_loop = TICK() - t_begin;
 
+    if constexpr (GROUPS) {
+      // ---- hand-off: every thread copies its own list -- entries with their final locator (segment bit | group index
+      //      inside the bank) and the 8 scores of each from the log -- into row (virtual split, query) of the exchange
+      //      arrays, four entries per step (one 32-byte store of entries, four of scores) ----
+      st.tau = fmaxf(st.tau, tau_sh[row]);
+      st = compact_list(st);
+      const int my_n = (int)((st.off - st.base) / SS);
+      const int q = qtile * TQ + row;
+      if (q < a.hw) a.cand_count[(int64_t)vsplit * a.hw_pad + q] = my_n;
+      const int64_t list = ((int64_t)vsplit * a.hw_pad + q) * GSLOTS;
+      float *ent_out = reinterpret_cast<float *>(a.cand + list);
+      float *rec_out = a.gscore + list * GROUP_KEYS;
+      const int nmax = __reduce_max_sync(FULL, my_n);
+      for (int e0 = 0; e0 < nmax; e0 += 4) {
+        Rec8 r[4], hd;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = e0 + u < my_n;
+          const Entry en = lds_entry(st.base + (in ? e0 + u : 0) * SS);
+          const uint32_t gix = en.index & GIDX_MASK;
+          const int64_t g = g_lo + (gix >> 3);
+          const uint32_t loc = g >= g_tiles0 ? (GROUP_SEG_BIT | (uint32_t)((g_tile1 + (g - g_tiles0)) * (TK / 8) + (gix & 7)))
+                                             : (uint32_t)((g_tile0 + g) * (TK / 8) + (gix & 7));
+          hd.w[2 * u] = __float_as_uint(en.score);
+          hd.w[2 * u + 1] = loc;
+          r[u] = ldg_rec(logp + (size_t)(in ? en.index >> GIDX_BITS : 0u) * GROUP_KEYS);
+        }
+        if (e0 < my_n) {
+          stg_rec(ent_out + e0 * 2, hd);   // (entries past my_n are never read: cand_count)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (e0 + u < my_n) stg_rec(rec_out + (size_t)(e0 + u) * GROUP_KEYS, r[u]);
+        }
+      }
+    } else
     // ---- hand the surviving candidates to the merge: both sets of a query share one exchange row, set 0 first.
     //      Lanes run over the entries of a row (coalesced 8-byte stores), four rows per step for ILP. ----
     {
@@ -788,6 +955,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       if (quarter == 0) { dbg[13] = t_loop; dbg[14] = TICK() - t_begin; }
       if (quarter == 1) dbg[15] = t_first;
       if (quarter == 0) { dbg[16] = t_ld; dbg[17] = t_max; dbg[18] = t_app; dbg[19] = n_active; dbg[20] = n_relieve; }
+      if (quarter == 0) { dbg[25] = t_x0; dbg[26] = t_x1; dbg[27] = n_done; }
     }
   }
 
@@ -870,7 +1038,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_tile_kernel(const unsigned
 
 thread_local long long *g_tc_debug = nullptr;  // set through vosmem_debug_set_timing_buffer (per host thread)
 
-int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, cudaStream_t st,
+int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int n, int splits, bool groups, cudaStream_t st,
                      const PeerThresholds *peers) {
   VOSMEM_CHECK_ARG(n >= 1 && n <= MAX_BATCH, "select(tcgen05): batch of %d problems outside [1, %d]", n, MAX_BATCH);
   TcBatch batch{};
@@ -917,7 +1085,14 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
     a.ctl = ws.ctl;
     a.cand = ws.cand;
     a.cand_count = ws.cand_count;
+    a.gscore = ws.gscore;
+    a.glog = ws.glog;
     a.dbg = g_tc_debug;
+    { const char *e = getenv("VOSMEM_TC_EXP"); a.exp = e ? atoi(e) : 0; }
+    if (groups)
+      for (int s = 0; s < d.n_segments; ++s)
+        VOSMEM_CHECK_ARG(d.seg[s].end < ((int64_t)1 << 31), "select(tcgen05): segment %d ends at key %lld (group locators hold 31 bits)",
+                         s, (long long)d.seg[s].end);
   }
   const vosmem_select_desc &d = descs[0];
   dim3 grid((unsigned)ceil_div64(d.hw, TQ), splits, n);
@@ -925,16 +1100,19 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
   const int r = (33 + HALVES * splits - 1) / (HALVES * splits);
   batch.r2 = (33 + HALVES * splits * batch.world - 1) / (HALVES * splits * batch.world);
   // the shared-memory opt-in is a per-device function attribute: set it on every launch (a host-side table lookup)
+  // (thresholds across ranks are only instantiated for single-key candidates: api.cu never asks for both)
+#define VOSMEM_LAUNCH_TC_AS(RR, SH, GR)                                                                          \
+  do {                                                                                                           \
+    VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR, SH, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
+    select_tc_kernel<RR, SH, GR><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                     \
+  } while (0)
 #define VOSMEM_LAUNCH_TC(RR)                                                                                     \
   do {                                                                                                           \
-    if (batch.world > 1) {                                                                                       \
-      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
-      select_tc_kernel<RR, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                     \
-    } else {                                                                                                     \
-      VOSMEM_CUDA(cudaFuncSetAttribute(select_tc_kernel<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)); \
-      select_tc_kernel<RR, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(batch);                                    \
-    }                                                                                                            \
+    if (batch.world > 1) VOSMEM_LAUNCH_TC_AS(RR, true, false);                                                   \
+    else if (groups) VOSMEM_LAUNCH_TC_AS(RR, false, true);                                                       \
+    else VOSMEM_LAUNCH_TC_AS(RR, false, false);                                                                  \
   } while (0)
+  VOSMEM_CHECK_ARG(!groups || batch.world == 1, "select(tcgen05): thresholds across ranks and group candidates together");
   if (r <= 1) VOSMEM_LAUNCH_TC(1);
   else if (r == 2) VOSMEM_LAUNCH_TC(2);
   else if (r == 3) VOSMEM_LAUNCH_TC(3);
@@ -942,6 +1120,7 @@ int launch_select_tc(const vosmem_select_desc *descs, const Workspace *wss, int 
   else if (r <= 6) VOSMEM_LAUNCH_TC(6);
   else if (r <= 9) VOSMEM_LAUNCH_TC(9);
   else VOSMEM_LAUNCH_TC(17);
+#undef VOSMEM_LAUNCH_TC_AS
 #undef VOSMEM_LAUNCH_TC
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
