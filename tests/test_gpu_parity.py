@@ -682,6 +682,48 @@ def test_peer_exchange_equals_nccl_exchange_on_two_gpus(vos):
     assert r.stdout.count('max |nccl - peer|') == 2 and r.stdout.count('vs unsharded') == 6
 
 
+def test_sharded_memory_manager_replays_the_lifecycle_on_two_gpus(vos):
+    """MemoryManager(config['vosmem_shard'] = 'n') on 2 ranks == the single-GPU manager == the reference's recorded
+    readouts, over the recorded lifecycles (consolidation, eviction, several object groups; memory_manager.py:57-150,
+    211-286).  Needs two GPUs; scripts/sharded_manager_check.py is the program."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29578',
+                        os.path.join(root, 'scripts', 'sharded_manager_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('vs single-GPU manager') == 8
+
+
+def test_sharded_memory_manager_on_one_rank(vos):
+    """The same code path with a world of one (runs on the driver's single-GPU box): a process group of size 1, the
+    lifecycle replay through ShardedMatch (candidate ranges, two index bases, usage deltas + sync) == the recorded
+    reference readouts."""
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29579')
+        dist.init_process_group('gloo', rank=0, world_size=1)
+        created = True
+    try:
+        for name in ('lifecycle_evict.npz', 'lifecycle_groups.npz'):
+            z = load(name)
+            cfg = dict(lifecycle_config(z), vosmem_value_dtype='fp32', vosmem_shard='n')
+            m = vos.MemoryManager(cfg)
+            single = vos.MemoryManager(dict(lifecycle_config(z), vosmem_value_dtype='fp32'))
+            got = replay_lifecycle(z, m, device='cuda')
+            replay_lifecycle(z, single, device='cuda')
+            m._sharded.sync_usage()
+            for i, g, want in got:
+                assert orc.rel_err(g.cpu(), want) < 2e-3, f'{name} event {i}'
+            assert orc.rel_err(m.work_mem.use_count.cpu(), single.work_mem.use_count.cpu()) < 1e-4
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_dense_softmax_twin_takes_large_top_k(vos):
     """memory_util.do_softmax accepts any top_k (memory_util.py:46); the dense twin serves k up to 512 (the fused
     per-frame path is limited to 32, checked at MemoryManager construction)."""

@@ -70,6 +70,14 @@ __global__ void __launch_bounds__(256, MB <= 4 ? 4 : 2) merge_push_kernel(const 
   signal_when_grid_done(a.ticket, a.flag, a.world, a.seq);
 }
 
+// A rank without keys launches no selection kernel; its workspace still has to step through the launch epochs in
+// step with the other ranks' (thresholds shared across ranks are validated by epoch: select_tc.cu).
+__global__ void bump_epoch_kernel(WsControl *ctl) {
+  const uint32_t epoch = ctl->epoch;
+  ctl->last = epoch;
+  ctl->epoch = epoch + 1u == 0u ? 1u : epoch + 1u;
+}
+
 struct SliceArgs {
   const float *src;
   int64_t src_ld, dst_ld;
@@ -145,7 +153,10 @@ extern "C" int vosmem_select_push(const vosmem_select_desc *select, const vosmem
   if (n_keys > 0) {
     int rc = run_selection_for_push(select, st, a.lists, shared ? &peers : nullptr);
     if (rc != VOSMEM_OK) return rc;
-  }   // else: no lists (splits == 0) -> every query's exchange list is pushed empty, the flags are raised as usual
+  } else {   // no lists (splits == 0): every query's exchange list is pushed empty, the flags are raised as usual
+    VOSMEM_CHECK_ARG(select->workspace != nullptr, "vosmem_select_push: null workspace");
+    bump_epoch_kernel<<<1, 1, 0, st>>>(static_cast<WsControl *>(select->workspace));
+  }
   const int n_lists = a.lists.splits;
   a.hw = select->hw;
   a.top_k = select->top_k;

@@ -13,7 +13,11 @@ over the [long-term | working] banks in place (no torch.cat of keys, similaritie
 memory_manager.py:73-74,83,92-93,105).  Usage counters are updated inside the readout kernel.
 
 Optional config keys (not in the reference's YAML): ``vosmem_value_dtype`` ('bf16' default | 'fp32') --
-storage type of the gather-friendly value shadow; ``vosmem_path`` ('auto' | 'simt' | 'tcgen05').
+storage type of the gather-friendly value shadow; ``vosmem_path`` ('auto' | 'simt' | 'tcgen05');
+``vosmem_shard`` = 'n' -- one tracker spread over the ranks of ``torch.distributed`` (one process per GPU): every
+rank keeps the banks (the ranks run the same add_memory calls) but scans only its N-shard of [long-term | working]
+keys per frame; candidates, readout and usage are exchanged as described in ``sharded.py`` (class
+``ShardedMatch`` below); results equal the single-GPU manager's.
 """
 from __future__ import annotations
 
@@ -71,6 +75,8 @@ class MemoryManager:
 
         self.reset_config = True
         self._scratch = None
+        # N-sharded over the ranks of torch.distributed (see the module docstring)
+        self._sharded = ShardedMatch(self, config) if str(config.get('vosmem_shard', '')).lower() == 'n' else None
 
     def update_config(self, config):
         self.reset_config = True
@@ -163,6 +169,8 @@ class MemoryManager:
         [1 x] num_objects x (CV + CH) x H x W buffer -- the decoder's concatenated input (model/modules.py:232-233) --
         whose channels [0, CV) receive the readout directly; the returned tensor is that view (``None``: a fresh
         num_objects x CV x H x W tensor).  See `readout_with_hidden`."""
+        if self._sharded is not None:
+            return self._sharded.match(query_key, selection, out)
         problems, out = self._plan_match(query_key, selection, out)
         hw = out.shape[-2] * out.shape[-1]
         if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != out.device:
@@ -208,6 +216,9 @@ class MemoryManager:
                     self.work_mem.reserve(self.max_work_elements + self.HW)
                 if self.max_long_elements + self.num_prototypes <= 1 << 20:
                     self.long_mem.reserve(self.max_long_elements + self.num_prototypes)
+
+        if self._sharded is not None:
+            self._sharded.sync_usage()     # consolidation / eviction below read the usage of ALL queries
 
         key = key.flatten(start_dim=2)
         shrinkage = shrinkage.flatten(start_dim=2)
@@ -297,6 +308,119 @@ class MemoryManager:
         prototype_shrinkage = (self._readout(affinity[0], candidate_shrinkage)
                                if candidate_shrinkage is not None else None)
         return prototype_key, prototype_value, prototype_shrinkage
+
+
+class ShardedMatch:
+    """``match_memory`` of ONE tracker spread over the ranks of ``torch.distributed`` (config ``vosmem_shard='n'``;
+    SURVEY.md section 8e; the reference is single-GPU, tools/runner.py:32).
+
+    Every rank holds the banks (the ranks run the same ``add_memory`` / consolidation calls on the same inputs, so
+    the replicas stay identical) but per frame scans only ITS 64-key aligned blocks of the long-term and the working
+    keys -- the two candidate segments of memory_manager.py:73-74, cut down per rank (``sharded.plan_shard_ranges``;
+    groups that entered late see suffixes, memory_manager.py:88-98).  ``ShardedLongTermReadout`` moves the candidate
+    lists to the ranks that own the queries, which merge them and read out their query slice from the (replicated)
+    values; the slices are gathered so that every rank returns the full ``num_objects x CV x h x w`` readout.
+
+    Usage (memory_manager.py:113-119): a rank's readout kernel adds the weights of ITS queries into rank-local
+    delta buffers; ``sync_usage`` all-reduces the deltas into ``use_count`` before anything reads the usage
+    (``add_memory`` -> ``remove_obsolete_features`` / ``compress_features``), which is every mem_every-th frame and
+    not per frame.  ``life_count`` is aged on every rank by the same kernel."""
+
+    def __init__(self, manager: 'MemoryManager', config):
+        import torch.distributed as dist
+        from .sharded import ShardedLongTermReadout
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("vosmem_shard='n' needs an initialised torch.distributed process group (one rank per GPU)")
+        self.m = manager
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        cfg = dict(config)
+        cfg['vosmem_shard'] = 'n'
+        self.engine = ShardedLongTermReadout(cfg, self.rank, self.world, self.device)
+        self.engine.backend.value_dtype = manager.value_dtype
+        self._delta = {}      # id(store) -> flat fp32 usage delta of this rank since the last sync
+
+    def _delta_of(self, store):
+        cap = store._use.capacity
+        d = self._delta.get(id(store))
+        if d is None or d[0].numel() < cap:
+            if d is not None:
+                self._sync_store(store, d[0])          # (capacity grew: fold what was accumulated first)
+            d = (torch.zeros(cap, dtype=torch.float32, device=store._use.buf.device), store)
+            self._delta[id(store)] = d
+        return d[0]
+
+    def _sync_store(self, store, delta):
+        import torch.distributed as dist
+        n = store._use.n
+        if n:
+            part = delta[:n]
+            if self.world > 1:
+                dist.all_reduce(part)
+            store._use.view().view(-1).add_(part)
+        delta.zero_()
+
+    def sync_usage(self):
+        """use_count += sum over ranks of the usage their query slices produced since the last call."""
+        for delta, store in list(self._delta.values()):
+            self._sync_store(store, delta)
+
+    def match(self, query_key, selection, out=None):
+        from .sharded import ShardProblem, plan_shard_ranges
+        m = self.m
+        work = m.work_mem
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        if query_key.shape[0] != 1:
+            raise RuntimeError('match_memory expects batch size 1 (inference_core.py:53)')
+        ops._need(query_key, 'query_key')
+        use_long = m.enable_long_term and m.long_mem.engaged()
+        long = m.long_mem if use_long else None
+        n_work, n_long = work.size, (long.size if use_long else 0)
+        track_work = use_long or m.enable_long_term
+        track_long = use_long and m.enable_long_term_usage
+        rows_total = sum(work.group_rows(gi) for gi in range(work.num_groups))
+        if out is None:
+            result = torch.empty((rows_total // m.CV, m.CV, h, w), dtype=torch.float32, device=query_key.device)
+            dst = result.view(rows_total, hw)
+        else:
+            if out.dim() == 5 and out.shape[0] == 1:
+                out = out[0]
+            result = out[:, :m.CV]
+            dst = None
+        row0 = 0
+        for gi in range(work.num_groups):
+            has_long = use_long and gi < long.num_groups
+            len_l = long.get_v_size(gi) if has_long else 0
+            len_w = n_work if gi == 0 else work.get_v_size(gi)
+            ranges = [(n_long - len_l, n_long), (n_work - len_w, n_work)] if has_long else [(n_work - len_w, n_work)]
+            sizes = [n_long, n_work] if has_long else [n_work]
+            mine, base0, seg0_len, base1, share_ok = plan_shard_ranges(ranges, sizes, self.world, self.rank)
+            banks = [long, work] if has_long else [work]
+            segments = [b.key_segment(lo, hi) for b, (lo, hi) in zip(banks, mine)]
+            values, first = [], 0
+            for b, (begin, end), tracked in zip(banks, ranges, [track_long, track_work] if has_long else [track_work]):
+                vg = b._groups[gi]
+                track = gi == 0 and tracked and b.count_usage
+                values.append(ops.ValueSegment(
+                    shadow=vg.shadow, first=first, count=vg.n,
+                    use_count=self._delta_of(b)[begin:] if track else None,
+                    life_count=b._life.buf.view(-1)[begin:] if track else None))
+                first += end - begin
+            rows = work.group_rows(gi)
+            prob = ShardProblem(segments, base0, seg0_len, base1, values, rows, first, share_ok)
+            full = self.engine.match(query_key, selection, gather=True, problem=prob)     # rows x HW
+            q_lo, q_hi = self.engine.query_range(hw)
+            if q_hi <= q_lo and gi == 0:        # this rank owns no query: its readout kernel (which ages) did not run
+                for b, tracked in zip(banks, [track_long, track_work] if has_long else [track_work]):
+                    if tracked:
+                        b.age()
+            if dst is not None:
+                dst[row0:row0 + rows].copy_(full)
+            else:
+                result[row0 // m.CV:(row0 + rows) // m.CV].copy_(full.view(rows // m.CV, m.CV, h, w))
+            row0 += rows
+        return result
 
 
 def match_memory_batch(managers, query_keys, selections):

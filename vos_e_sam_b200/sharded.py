@@ -31,7 +31,8 @@ on the oracle); the product backend is ``CudaBackend`` -- kernels of libvosmem.s
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Tuple
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -59,6 +60,44 @@ def partition_sequences(n_sequences: int, world: int, rank: int) -> List[int]:
     return list(range(rank, n_sequences, world))
 
 
+@dataclass
+class ShardProblem:
+    """One object group of a sharded ``MemoryManager.match_memory`` call, as this rank sees it."""
+    segments: list          # ops.KeySegment: this rank's part of [long-term | working] candidate keys (may be empty ranges)
+    index_base: int         # local candidate i < seg0_len  -> global candidate i + index_base
+    seg0_len: int
+    index_base1: int        # local candidate i >= seg0_len -> global candidate i - seg0_len + index_base1
+    values: list            # ops.ValueSegment on the GLOBAL candidate axis (banks are replicated)
+    rows: int
+    n_total: int
+    share_ok: bool = True   # every rank scans at least one key (thresholds across ranks need all kernels running)
+
+
+def plan_shard_ranges(ranges: Sequence[Tuple[int, int]], sizes: Sequence[int], world: int, rank: int
+                      ) -> Tuple[List[Tuple[int, int]], int, int, int, bool]:
+    """Candidate ranges of one object group, [begin_b, size_b) of every bank b (memory_manager.py:83,88-98: a group that
+    entered late sees a suffix), cut down to what `rank` scans: bank b is dealt to the ranks in 64-key aligned blocks of
+    its whole key axis (``shard_bounds(size_b, world, rank)``), so the blocks do not move while a group's suffix does.
+    Returns (this rank's [lo, hi) per bank, index_base, seg0_len, index_base1, every rank has a key) with the GLOBAL
+    candidate axis = the concatenated full ranges."""
+    mine, counts = [], [0] * world
+    for (begin, end), size in zip(ranges, sizes):
+        assert end == size and 0 <= begin <= end
+        for r in range(world):
+            lo, hi = shard_bounds(size, world, r)
+            lo, hi = max(lo, begin), max(hi, max(lo, begin))
+            counts[r] += hi - lo
+            if r == rank:
+                mine.append((lo, hi))
+    first = [0]
+    for (begin, end) in ranges[:-1]:
+        first.append(first[-1] + end - begin)
+    index_base = mine[0][0] - ranges[0][0]
+    seg0_len = mine[0][1] - mine[0][0]
+    index_base1 = first[1] + mine[1][0] - ranges[1][0] if len(ranges) > 1 else 0
+    return mine, index_base, (seg0_len if len(ranges) > 1 else -1), index_base1, all(c > 0 for c in counts)
+
+
 class CudaBackend:
     """The product backend: every call is a libvosmem.so kernel on the current CUDA stream."""
 
@@ -74,8 +113,10 @@ class CudaBackend:
     def load_keys(self, key, shrinkage):
         self.keys = self.store_cls(count_usage=False, value_dtype=self.value_dtype)
         # the key bank carries no values of its own here (values are replicated separately)
-        self.keys.add(key.to(self.device), [], shrinkage.to(self.device), None, None)
         self.n_keys = key.shape[-1]
+        if self.n_keys == 0:     # empty shard: the store holds one key that no candidate range ever covers
+            key, shrinkage = torch.zeros((1, key.shape[1], 1)), torch.ones((1, 1, 1))
+        self.keys.add(key.to(self.device), [], shrinkage.to(self.device), None, None)
 
     def load_values(self, value):
         """value: n_obj x CV x N (full bank, replicated)."""
@@ -95,33 +136,38 @@ class CudaBackend:
         self.N.check(self.N.lib.vosmem_workspace_init(ws.data_ptr(), ws.numel(), self.ops._stream()), 'vosmem_workspace_init')
 
     def select_push(self, qk, qe, top_k, index_base, per, world, rank, dst_ptrs, flag_ptrs, seq, ticket_ptr, send=None,
-                    workspace=None, rank_pub_ptrs=None):
+                    workspace=None, rank_pub_ptrs=None, segments=None, seg0_len=-1, index_base1=0):
         """Local selection over this rank's keys + push of every query's list to its owner (one C call, two launches).
         `send`: the tensor behind dst_ptrs in collective mode (unused here: the kernel takes the raw addresses).
         `workspace`: the engine's own (peer-mapped) scratch; `rank_pub_ptrs`: every rank's threshold summary array
-        (thresholds shared across the ranks while the kernels run), or None."""
+        (thresholds shared across the ranks while the kernels run), or None.
+        `segments`: this rank's candidate ranges as ops.KeySegment ([long-term shard | working-memory shard] of a
+        sharded MemoryManager; None: the bank loaded with load_keys); local candidate i of them becomes global index
+        i + index_base for i < seg0_len, i - seg0_len + index_base1 otherwise (seg0_len < 0: one base)."""
         N, ops = self.N, self.ops
         push = N.PushDesc()
         push.world, push.rank, push.per, push.index_base = world, rank, per, index_base
+        push.seg0_len, push.index_base1 = seg0_len, index_base1
         for r in range(world):
             push.dst[r] = dst_ptrs[r]
             push.flag[r] = flag_ptrs[r] if flag_ptrs is not None else None
             push.rank_pub[r] = rank_pub_ptrs[r] if rank_pub_ptrs is not None else None
         push.seq, push.ticket = seq, ticket_ptr
         keep: list = []
-        if self.n_keys == 0:
-            raise RuntimeError('CudaBackend.select_push: this rank\'s key shard is empty (use fewer ranks or a larger bank)')
-        seg = [self.keys.key_segment(0, self.n_keys)]
-        sd = ops._select_desc(qk, qe, seg, top_k, 0, N.PATH_AUTO, keep, workspace=workspace)
+        if segments is None:     # (an empty shard pushes empty lists: vosmem_select_push)
+            segments = [self.keys.key_segment(0, self.n_keys)]
+        sd = ops._select_desc(qk, qe, segments, top_k, 0, N.PATH_AUTO, keep, workspace=workspace)
         N.check(N.lib.vosmem_select_push(C.byref(sd), C.byref(push), ops._stream()), 'vosmem_select_push')
 
     def exchange_readout(self, lists_ptr, n_lists, list_stride, first_entry, flags_ptr, seq, status_ptr, n_q, top_k, rows,
-                         n_total, out, lists=None):
+                         n_total, out, lists=None, values=None):
         """out: rows x n_q view (row pitch = out.stride(0)) of this rank's query slice.  `lists`: the tensor behind
-        lists_ptr in collective mode (unused here)."""
+        lists_ptr in collective mode (unused here).  `values`: ops.ValueSegment list on the GLOBAL candidate axis
+        (None: the replicated bank of load_values)."""
         N, ops = self.N, self.ops
-        seg = ops.ValueSegment(shadow=self.values, first=0, count=n_total, use_count=None)
-        rd = ops._readout_desc(n_q, top_k, rows, [seg], out, None)
+        if values is None:
+            values = [ops.ValueSegment(shadow=self.values, first=0, count=n_total, use_count=None)]
+        rd = ops._readout_desc(n_q, top_k, rows, values, out, None)
         x = N.ExchangeDesc()
         x.lists, x.n_lists, x.list_stride, x.first_entry = lists_ptr, n_lists, list_stride, first_entry
         x.flags, x.seq, x.status = flags_ptr, seq, status_ptr
@@ -145,7 +191,7 @@ class _Layout:
     CONTROL = 4096          # list flags [2][16] u32 @0, output flags [2][16] u32 @128, tickets @256/@260, status @264
 
     def __init__(self, world: int, per: int, rows: int, hw: int, with_output: bool, ws_bytes: int = 0):
-        self.world, self.per = world, per
+        self.world, self.per, self.hw = world, per, hw
         self.hw_pad = -(-hw // 128) * 128
         self.rank_pub0 = self.CONTROL                              # [world][hw_pad] x 8 B threshold summaries
         self.rank_pub_bytes = -(-world * self.hw_pad * 8 // 256) * 256
@@ -203,16 +249,15 @@ class ShardedLongTermReadout:
         """key 1 x CK x N, shrinkage 1 x 1 x N, value n_obj x CV x N: the whole bank; this rank keeps keys [lo, hi)."""
         self.n_total = key.shape[-1]
         self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank) if self.shard == 'n' else (0, self.n_total)
-        if self.hi > self.lo:
-            self.backend.load_keys(key[:, :, self.lo:self.hi], shrinkage[:, :, self.lo:self.hi])
-        else:   # an empty shard still answers every query with an empty list: one key that can never be selected
-            self.backend.load_keys(key[:, :, :0], shrinkage[:, :, :0])
+        # (an empty shard still answers every query, with empty lists)
+        self.backend.load_keys(key[:, :, self.lo:self.hi], shrinkage[:, :, self.lo:self.hi])
         self.rows = self.backend.load_values(value)
 
     def _buffers(self, hw: int, with_output: bool):
         """Exchange buffer of this rank, peer-mapped on every rank in 'peer' mode (allocated on first use: collective)."""
         per = query_slices(hw, self.world)
-        if self._buf is not None and self._buf[0].per == per and (self._buf[0].out_bytes > 0 or not with_output):
+        if self._buf is not None and self._buf[0].per == per and self._buf[0].hw == hw and \
+                (self._buf[0].out_bytes >= self.rows * hw * 4 or not with_output):
             return self._buf
         peer = self.exchange == 'peer' and self.world > 1
         ws_bytes = self.backend.workspace_bytes(64, hw) if peer and hasattr(self.backend, 'workspace_bytes') else 0
@@ -238,14 +283,26 @@ class ShardedLongTermReadout:
         return min(hw, self.rank * per), min(hw, (self.rank + 1) * per)
 
     # ------------------------------------------------------------------------------------------------
-    def match(self, query_key, selection, events=None, gather: bool = True) -> torch.Tensor:
+    def match(self, query_key, selection, events=None, gather: bool = True, problem: Optional['ShardProblem'] = None
+              ) -> torch.Tensor:
         """query_key / selection: 1 x CK x h x w.  gather=True -> rows x HW (the full readout on every rank);
         gather=False -> rows x (q_hi - q_lo), this rank's query slice (``query_range``).
-        events (optional, for bench.py): [after local select + push, after exchange + readout, after gather]."""
+        events (optional, for bench.py): [after local select + push, after exchange + readout, after gather].
+        problem (optional): this rank's candidate ranges and the value segments of the call (a sharded
+        MemoryManager passes its banks); None = the bank given to ``load_long_term``."""
         h, w = query_key.shape[-2:]
         hw = h * w
         qk = query_key.flatten(start_dim=2)[0]
         qe = selection.flatten(start_dim=2)[0] if selection is not None else None
+        if problem is not None:
+            assert self.shard == 'n'
+            self.rows = max(self.rows, problem.rows)     # sizes the (symmetric) output buffers
+        rows = problem.rows if problem is not None else self.rows
+        sel_kw = dict(segments=problem.segments, seg0_len=problem.seg0_len, index_base1=problem.index_base1) \
+            if problem is not None else {}
+        rd_kw = dict(values=problem.values) if problem is not None else {}
+        index_base = problem.index_base if problem is not None else self.lo
+        n_total = problem.n_total if problem is not None else self.n_total
         if self.shard == 'queries':
             return self._match_query_sharded(qk, qe, hw, events, gather)
         be, k, G, r = self.backend, self.top_k, self.world, self.rank
@@ -261,16 +318,17 @@ class ShardedLongTermReadout:
         if peer:
             dst = [bases[d] + lay.lists(slot, r) for d in range(G)]
             flags = [bases[d] + lay.list_flag(slot, r) for d in range(G)]
-            share = self.share_thresholds and lay.ws_bytes > 0 and qk.shape[0] == 64
-            be.select_push(qk, qe, k, self.lo, per, G, r, dst, flags, seq, me + lay.ticket_push,
+            share = self.share_thresholds and lay.ws_bytes > 0 and qk.shape[0] == 64 and \
+                (problem is None or problem.share_ok)
+            be.select_push(qk, qe, k, index_base, per, G, r, dst, flags, seq, me + lay.ticket_push,
                            workspace=buf[lay.ws0:lay.ws0 + lay.ws_bytes] if lay.ws_bytes else None,
-                           rank_pub_ptrs=[bases[d] + lay.rank_pub0 for d in range(G)] if share else None)
+                           rank_pub_ptrs=[bases[d] + lay.rank_pub0 for d in range(G)] if share else None, **sel_kw)
         else:
             if self._send is None or self._send.numel() != lay.slot_bytes:
                 self._send = be.new_buffer(lay.slot_bytes)
             send = self._send
             dst = [send.data_ptr() + d * lay.list_bytes for d in range(G)]
-            be.select_push(qk, qe, k, self.lo, per, G, r, dst, None, seq, me + lay.ticket_push, send=send)
+            be.select_push(qk, qe, k, index_base, per, G, r, dst, None, seq, me + lay.ticket_push, send=send, **sel_kw)
         if events is not None:
             events[0].record()
 
@@ -285,13 +343,13 @@ class ShardedLongTermReadout:
             flags_ptr = None
         n_q = q_hi - q_lo
         if gather and peer:
-            full = buf[lay.out(slot):lay.out(slot) + lay.out_bytes].view(torch.float32).view(self.rows, hw)
+            full = buf[lay.out(slot):lay.out(slot) + rows * hw * 4].view(torch.float32).view(rows, hw)
         else:
-            full = torch.empty((self.rows, hw if gather else max(n_q, 1)), dtype=torch.float32, device=qk.device)
+            full = torch.empty((rows, hw if gather else max(n_q, 1)), dtype=torch.float32, device=qk.device)
         mine = full[:, q_lo:q_hi] if gather else full[:, :n_q]
         if n_q > 0:
-            be.exchange_readout(lists_ptr, G, per * EXCH_K, 0, flags_ptr, seq, me + lay.status, n_q, k, self.rows,
-                                self.n_total, mine, lists=lists)
+            be.exchange_readout(lists_ptr, G, per * EXCH_K, 0, flags_ptr, seq, me + lay.status, n_q, k, rows,
+                                n_total, mine, lists=lists, **rd_kw)
         if events is not None:
             events[1].record()
         if not gather:
@@ -309,10 +367,10 @@ class ShardedLongTermReadout:
             if mask:                # ranks whose query slice is empty push nothing
                 be.wait_flags(me + lay.out_flag(slot), mask, seq, me + lay.status)
         elif G > 1:
-            part = torch.zeros((self.rows, per), dtype=torch.float32, device=qk.device)
+            part = torch.zeros((rows, per), dtype=torch.float32, device=qk.device)
             part[:, :n_q] = mine
             gathered = self._all_gather(part)                                   # world x rows x per
-            full = gathered.permute(1, 0, 2).reshape(self.rows, G * per)[:, :hw]
+            full = gathered.permute(1, 0, 2).reshape(rows, G * per)[:, :hw]
         if events is not None:
             events[2].record()
         return full
