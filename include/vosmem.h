@@ -281,6 +281,26 @@ int vosmem_readout_dense(const float *value, int64_t value_ld, const float *affi
                          int64_t n, int hw, float *out, int64_t out_ld, vosmem_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * KeyProjection (tracker/model/modules.py:194-211): key_proj, d_proj and e_proj -- three 3x3 convolutions (padding 1)
+ * of the 1/16-scale feature map, the producers of the query key / shrinkage / selection that the readout consumes
+ * (tracker/model/network.py:55) -- as ONE implicit GEMM with 2 * key_dim + 1 output channels on tcgen05 (bf16 hi / lo
+ * split, ~fp32 accuracy).  key_dim == 64, in_dim a multiple of 32 (XMem: 1024), batch 1, w <= 240.
+ * ------------------------------------------------------------------------------------------- */
+
+/* bytes of the packed weights for vosmem_keyproj_pack_weights (0: unsupported dimensions) */
+int64_t vosmem_keyproj_weight_bytes(int in_dim, int key_dim);
+/* key_w: key_dim x in_dim x 3 x 3, d_w: 1 x in_dim x 3 x 3, e_w: key_dim x in_dim x 3 x 3 (nn.Conv2d layout).  Once per model. */
+int vosmem_keyproj_pack_weights(const float *key_w, const float *d_w, const float *e_w, int in_dim, int key_dim,
+                                void *packed, vosmem_stream_t stream);
+int64_t vosmem_keyproj_workspace_bytes(int in_dim, int key_dim, int h, int w);
+/* x: in_dim x h x w.  key: key_dim x h x w = key_proj(x); shrinkage: h x w = d_proj(x)^2 + 1 or NULL (need_s false);
+ * selection: key_dim x h x w = sigmoid(e_proj(x)) or NULL (need_e false)  (modules.py:206-211). */
+int vosmem_keyproj_forward(const float *x, int in_dim, int key_dim, int h, int w, const void *packed_weights,
+                           const float *key_bias, const float *d_bias, const float *e_bias, float *key,
+                           float *shrinkage, float *selection, void *workspace, int64_t workspace_bytes,
+                           vosmem_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Self-test hook: D[128 x 64] = A[128 x 272] . B[64 x 272]^T through the same descriptors the
  * tcgen05 path uses, on packed images.  Returns the raw accumulator tile (fp32, 128 x 64).
  * ------------------------------------------------------------------------------------------- */

@@ -255,10 +255,38 @@ def lifecycle(name, cfg, frames, hw, cv, new_object_at=None):
           'groups', mm.work_mem.num_groups)
 
 
+def keyproj_cases():
+    """The reference's KeyProjection module (tracker/model/modules.py:194-211) on seeded parameters and inputs.  Only the
+    outputs are stored: tests/synth.keyproj_params and the input are regenerated from the same seeds by the tests."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests import synth
+    from model.modules import KeyProjection
+    out = {}
+    for name, in_dim, h, w in (('small', 64, 5, 7), ('xmem', 1024, 12, 20)):
+        g = torch.Generator().manual_seed(500 + in_dim)
+        prm = synth.keyproj_params(g, in_dim)
+        x = rnd(g, 1, in_dim, h, w)
+        mod = KeyProjection(in_dim, CK)
+        with torch.no_grad():
+            mod.key_proj.weight.copy_(prm['key_w']); mod.key_proj.bias.copy_(prm['key_b'])
+            mod.d_proj.weight.copy_(prm['d_w']); mod.d_proj.bias.copy_(prm['d_b'])
+            mod.e_proj.weight.copy_(prm['e_w']); mod.e_proj.bias.copy_(prm['e_b'])
+            key, shrinkage, selection = mod(x, True, True)
+            key_only = mod(x, False, False)
+        assert key_only[1] is None and key_only[2] is None and torch.equal(key_only[0], key)
+        out[f'{name}/shape'] = torch.tensor([in_dim, h, w])
+        out[f'{name}/key'], out[f'{name}/shrinkage'], out[f'{name}/selection'] = key, shrinkage, selection
+    np.savez_compressed(os.path.join(OUT, 'keyproj_cases.npz'), **{a: b.numpy() for a, b in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # bit-stable reductions for the committed vectors
+    if '--keyproj-only' in sys.argv:
+        keyproj_cases()
+        return
     util_cases()
+    keyproj_cases()
     match_cases()
     # single group, small long-term budget -> compression + least-used eviction
     lifecycle('evict', base_config(top_k=8, mem_every=2, num_prototypes=32, max_long_term_elements=80),

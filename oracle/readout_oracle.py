@@ -478,6 +478,18 @@ class Readout:
 # ---------------------------------------------------------------------------
 # parity rule helpers (BASELINE.json north_star)
 # ---------------------------------------------------------------------------
+def key_projection(x: Tensor, key_w: Tensor, key_b: Tensor, d_w: Tensor, d_b: Tensor, e_w: Tensor, e_b: Tensor,
+                   need_s: bool = True, need_e: bool = True):
+    """KeyProjection.forward (tracker/model/modules.py:206-211): three 3x3 convolutions with padding 1 of
+    x (B x in_dim x h x w); shrinkage = d_proj(x)^2 + 1, selection = sigmoid(e_proj(x)).  Works in the dtype of x
+    (fp32 = the contract, fp64 for error measurements)."""
+    conv = torch.nn.functional.conv2d
+    key = conv(x, key_w.to(x.dtype), key_b.to(x.dtype), padding=1)
+    shrinkage = conv(x, d_w.to(x.dtype), d_b.to(x.dtype), padding=1) ** 2 + 1 if need_s else None
+    selection = torch.sigmoid(conv(x, e_w.to(x.dtype), e_b.to(x.dtype), padding=1)) if need_e else None
+    return key, shrinkage, selection
+
+
 def topk_gap(sim64: Tensor, k: int) -> Tensor:
     """Gap between the k-th and (k+1)-th largest fp64 similarity per query column."""
     kk = min(k + 1, sim64.shape[1])

@@ -24,3 +24,11 @@ def query(gen, h, w, ck=CK):
     qk = torch.randn(1, ck, h, w, generator=gen)
     qe = torch.sigmoid(torch.randn(1, ck, h, w, generator=gen))
     return qk, qe
+
+
+def keyproj_params(gen, in_dim, keydim=CK):
+    """Seeded KeyProjection parameters (modules.py:198-202 shapes) at the scale of a trained projection: outputs ~ N(0,1)."""
+    sc = (in_dim * 9) ** -0.5
+    return dict(key_w=torch.randn(keydim, in_dim, 3, 3, generator=gen) * sc, key_b=torch.randn(keydim, generator=gen) * 0.1,
+                d_w=torch.randn(1, in_dim, 3, 3, generator=gen) * sc, d_b=torch.randn(1, generator=gen) * 0.1,
+                e_w=torch.randn(keydim, in_dim, 3, 3, generator=gen) * sc, e_b=torch.randn(keydim, generator=gen) * 0.1)

@@ -106,3 +106,21 @@ def test_parity_helpers():
     perm = idx[torch.randperm(5, generator=g)]
     assert bool(orc.index_sets_equal(idx, perm).all())
     assert orc.rel_err(sim, sim) == 0.0
+
+
+@pytest.mark.parametrize('name', ['small', 'xmem'])
+def test_key_projection_oracle_vs_reference_module(name):
+    """oracle.key_projection == the reference's KeyProjection module (tracker/model/modules.py:194-211) on the seeded
+    parameters / input that oracle/gen_golden.py used."""
+    from tests import synth
+    z = load('keyproj_cases.npz')
+    in_dim, h, w = (int(v) for v in z[f'{name}/shape'])
+    g = torch.Generator().manual_seed(500 + in_dim)
+    prm = synth.keyproj_params(g, in_dim)
+    x = torch.randn(1, in_dim, h, w, generator=g)
+    key, shrinkage, selection = orc.key_projection(x, **prm)
+    torch.testing.assert_close(key, t(z[f'{name}/key']), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(shrinkage, t(z[f'{name}/shrinkage']), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(selection, t(z[f'{name}/selection']), rtol=1e-4, atol=1e-5)
+    key_only = orc.key_projection(x, **prm, need_s=False, need_e=False)
+    assert key_only[1] is None and key_only[2] is None

@@ -67,6 +67,10 @@ SIGNATURES = {
     'vosmem_key_image_bytes': (i64, [C.c_int, i64]),
     'vosmem_workspace_bytes': (i64, [C.c_int, C.c_int, i64]),
     'vosmem_query_image_bytes': (i64, [C.c_int, C.c_int]),
+    'vosmem_keyproj_weight_bytes': (i64, [C.c_int, C.c_int]),
+    'vosmem_keyproj_pack_weights': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    'vosmem_keyproj_workspace_bytes': (i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'vosmem_keyproj_forward': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'vosmem_workspace_init': (C.c_int, [vp, i64, vp]),
     'vosmem_workspace_status': (C.c_int, [vp, vp]),
     'vosmem_pack_keys': (C.c_int, [vp, i64, vp, C.c_int, i64, i64, vp, i64, vp]),

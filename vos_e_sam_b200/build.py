@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libvosmem.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
-SOURCES = ['api.cu', 'pack.cu', 'select_simt.cu', 'select_tc.cu', 'readout.cu', 'dense.cu', 'exchange.cu']
+SOURCES = ['api.cu', 'pack.cu', 'select_simt.cu', 'select_tc.cu', 'readout.cu', 'dense.cu', 'exchange.cu', 'keyproj.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-I', INCLUDE]
 

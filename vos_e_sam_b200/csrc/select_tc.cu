@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
   const int64_t g_hi = a.tiles_total * (blockIdx.y + 1) / a.splits;
   const int n_tiles = (int)(g_hi - g_lo);
   long long *dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 : nullptr;
+  if (a.exp & 4) return;   // experiment: launch + scheduling cost of this grid alone
   const long long t_entry = TICK();
   unsigned long long g_entry = 0;
   if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
