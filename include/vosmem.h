@@ -275,10 +275,24 @@ int vosmem_similarity_dense(const float *key, int64_t key_ld, const float *shrin
 int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k, float *affinity,
                          int64_t aff_ld, float *usage, vosmem_stream_t stream);
 
+/* The same with an optional scratch of vosmem_softmax_dense_scratch_bytes(n, hw) bytes: the dense (top_k <= 0) softmax
+ * then runs parallel over the key axis as well (two launches; a consolidation's 8 100 x 128 matrix: 630 -> ~15 us). */
+int64_t vosmem_softmax_dense_scratch_bytes(int64_t n, int hw);
+int vosmem_softmax_dense_ws(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k, float *affinity,
+                            int64_t aff_ld, float *usage, void *scratch, int64_t scratch_bytes, vosmem_stream_t stream);
+
 /* readout / MemoryManager._readout (memory_util.py:73-80, memory_manager.py:53-55):
  * out[rows x hw] = value[rows x n] @ affinity[n x hw] */
 int vosmem_readout_dense(const float *value, int64_t value_ld, const float *affinity, int64_t aff_ld, int rows,
                          int64_t n, int hw, float *out, int64_t out_ld, vosmem_stream_t stream);
+
+/* The dense readout on tcgen05 (bf16 hi / lo split of both operands, split-K, fp32 accumulation in tensor memory), for
+ * the shapes of a consolidation (memory_manager.py:280-284: 2 560 x 8 100 @ 8 100 x 128).  hw <= 256; `workspace` of
+ * vosmem_readout_dense_tc_workspace_bytes(rows, n, hw) bytes (0: shape not supported, use vosmem_readout_dense). */
+int64_t vosmem_readout_dense_tc_workspace_bytes(int rows, int64_t n, int hw);
+int vosmem_readout_dense_tc(const float *value, int64_t value_ld, const float *affinity, int64_t aff_ld, int rows,
+                            int64_t n, int hw, float *out, int64_t out_ld, void *workspace, int64_t workspace_bytes,
+                            vosmem_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * KeyProjection (tracker/model/modules.py:194-211): key_proj, d_proj and e_proj -- three 3x3 convolutions (padding 1)

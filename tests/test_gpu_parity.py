@@ -724,6 +724,33 @@ def test_sharded_memory_manager_on_one_rank(vos):
             dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('rows,n,hw', [(2560, 8100, 128), (200, 1000, 77), (640, 4000, 200), (64, 256, 1), (3, 500, 128)])
+def test_dense_readout_consolidation_shapes_vs_fp64(vos, rows, n, hw):
+    """MemoryManager._readout as consolidation calls it (memory_manager.py:53-55,280-285): value rows taken as a slice
+    of a longer bank (row pitch > n), the tcgen05 split-K product for large shapes, the few-rows kernel for the
+    shrinkage row.  Against an fp64 product; the bf16 hi / lo split keeps ~16 bits per factor."""
+    g = torch.Generator().manual_seed(rows + n)
+    bank = torch.randn(rows, n + 300, generator=g)
+    aff = torch.softmax(torch.randn(n, hw, generator=g) * 3, dim=0)
+    v = bank.cuda()[:, 100:100 + n]
+    got = vos.ops.readout_dense(v, aff.cuda())
+    torch.cuda.synchronize()
+    want = bank[:, 100:100 + n].double() @ aff.double()
+    assert got.shape == (rows, hw)
+    assert float((got.cpu().double() - want).abs().max()) < 5e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize('n,hw', [(8100, 128), (300, 45), (129, 1), (5000, 70)])
+def test_dense_softmax_parallel_over_rows(vos, n, hw):
+    """do_softmax(top_k=None) (memory_util.py:55-60) through the row-parallel statistics + apply kernels, with usage."""
+    g = torch.Generator().manual_seed(n)
+    sim = torch.randn(1, n, hw, generator=g) * 4
+    aff, usage = vos.do_softmax(sim.cuda(), top_k=None, return_usage=True)
+    want = torch.softmax(sim.double(), dim=1)
+    torch.testing.assert_close(aff.cpu().double(), want, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(usage.cpu().double(), want.sum(dim=2), rtol=1e-5, atol=1e-6)
+
+
 def test_dense_softmax_twin_takes_large_top_k(vos):
     """memory_util.do_softmax accepts any top_k (memory_util.py:46); the dense twin serves k up to 512 (the fused
     per-frame path is limited to 32, checked at MemoryManager construction)."""

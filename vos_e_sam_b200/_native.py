@@ -67,6 +67,10 @@ SIGNATURES = {
     'vosmem_key_image_bytes': (i64, [C.c_int, i64]),
     'vosmem_workspace_bytes': (i64, [C.c_int, C.c_int, i64]),
     'vosmem_query_image_bytes': (i64, [C.c_int, C.c_int]),
+    'vosmem_softmax_dense_scratch_bytes': (i64, [i64, C.c_int]),
+    'vosmem_softmax_dense_ws': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, vp, i64, vp, vp, i64, vp]),
+    'vosmem_readout_dense_tc_workspace_bytes': (i64, [C.c_int, i64, C.c_int]),
+    'vosmem_readout_dense_tc': (C.c_int, [vp, i64, vp, i64, C.c_int, i64, C.c_int, vp, i64, vp, i64, vp]),
     'vosmem_keyproj_weight_bytes': (i64, [C.c_int, C.c_int]),
     'vosmem_keyproj_pack_weights': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     'vosmem_keyproj_workspace_bytes': (i64, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -163,6 +163,90 @@ __global__ void __launch_bounds__(1024) softmax_full_dense_kernel(const float *s
   }
 }
 
+// Dense softmax over the key axis in two launches that are parallel over BOTH axes (the one-warp-per-column kernel above
+// leaves all but hw / 32 SMs idle: 630 us for the 8 100 x 128 matrix of a consolidation).  Rows are read as 128-byte
+// segments (lane = column of a group of 32).
+//   stats : per (row chunk, column) running max m and sum of exp(s - m)
+//   apply : combine the chunks' statistics per column, write exp(s - M) / S, add the row sums to `usage`
+constexpr int SM_ROWS = 128;    // rows per chunk
+__global__ void __launch_bounds__(256) softmax_stats_kernel(const float *__restrict__ sim, int64_t sim_ld, int64_t n, int hw,
+                                                            float2 *__restrict__ stats) {
+  __shared__ float2 part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * SM_ROWS;
+  float m = -INFINITY, sum = 0.f;
+  if (q < hw) {
+    for (int64_t i = r0 + warp; i < r0 + SM_ROWS && i < n; i += 8) {
+      const float v = sim[i * sim_ld + q];
+      const float nm = fmaxf(m, v);
+      sum = sum * expf(m - nm) + expf(v - nm);
+      m = nm;
+    }
+  }
+  part[warp][lane] = make_float2(m, sum);
+  __syncthreads();
+  if (warp == 0 && q < hw) {
+    float M = -INFINITY;
+    for (int w8 = 0; w8 < 8; ++w8) M = fmaxf(M, part[w8][lane].x);
+    float S = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8)
+      if (part[w8][lane].y > 0.f) S += part[w8][lane].y * expf(part[w8][lane].x - M);
+    stats[(int64_t)blockIdx.y * hw + q] = make_float2(M, S);
+  }
+}
+__global__ void __launch_bounds__(256) softmax_apply_kernel(const float *sim, int64_t sim_ld, int64_t n, int hw,
+                                                            const float2 *__restrict__ stats, int chunks, float *affinity,
+                                                            int64_t aff_ld, float *usage) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * SM_ROWS;
+  float M = -INFINITY, S = 0.f;
+  if (q < hw) {
+    for (int c = 0; c < chunks; ++c) M = fmaxf(M, stats[(int64_t)c * hw + q].x);
+    for (int c = 0; c < chunks; ++c) {
+      const float2 st = stats[(int64_t)c * hw + q];
+      if (st.y > 0.f) S += st.y * expf(st.x - M);
+    }
+  }
+  for (int64_t i = r0 + warp; i < r0 + SM_ROWS && i < n; i += 8) {
+    float w = 0.f;
+    if (q < hw) {
+      w = expf(sim[i * sim_ld + q] - M) / S;
+      affinity[i * aff_ld + q] = w;
+    }
+    if (usage) {
+      const float row = warp_sum(w);
+      if (lane == 0) atomicAdd(usage + i, row);
+    }
+  }
+}
+
+// out[rows x hw] = value[rows x n] @ affinity[n x hw] for a handful of rows (the shrinkage row of a consolidation,
+// memory_manager.py:285): the 64 x 64 tiles of the kernel below would run on hw / 64 CTAs.  grid = (column groups of 32,
+// row chunks of the key axis); partial sums are added into the zero-initialised output.
+__global__ void __launch_bounds__(256) readout_few_rows_kernel(const float *__restrict__ value, int64_t value_ld,
+                                                               const float *__restrict__ aff, int64_t aff_ld, int rows,
+                                                               int64_t n, int hw, float *__restrict__ out, int64_t out_ld) {
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * SM_ROWS;
+  for (int r = 0; r < rows; ++r) {
+    float acc = 0.f;
+    if (q < hw)
+      for (int64_t i = r0 + warp; i < r0 + SM_ROWS && i < n; i += 8) acc = fmaf(value[(int64_t)r * value_ld + i], aff[i * aff_ld + q], acc);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && q < hw) {
+      float t = 0.f;
+      for (int w8 = 0; w8 < 8; ++w8) t += part[w8][lane];
+      atomicAdd(out + (int64_t)r * out_ld + q, t);
+    }
+    __syncthreads();
+  }
+}
+
 // out[rows x hw] = value[rows x n] @ affinity[n x hw]
 __global__ void __launch_bounds__(256) readout_dense_kernel(const float *__restrict__ value, int64_t value_ld,
                                                             const float *__restrict__ aff, int64_t aff_ld, int rows,
@@ -211,6 +295,8 @@ __global__ void __launch_bounds__(256) readout_dense_kernel(const float *__restr
 
 using namespace vosmem;
 
+extern "C" int64_t vosmem_softmax_dense_scratch_bytes(int64_t n, int hw);
+
 extern "C" int vosmem_similarity_dense(const float *key, int64_t key_ld, const float *shrinkage,
                                        const float *query_key, const float *query_selection, int ck, int64_t n, int hw,
                                        float *out, vosmem_stream_t stream) {
@@ -224,9 +310,12 @@ extern "C" int vosmem_similarity_dense(const float *key, int64_t key_ld, const f
   return VOSMEM_OK;
 }
 
-extern "C" int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k,
-                                    float *affinity, int64_t aff_ld, float *usage, vosmem_stream_t stream) {
+// scratch (optional, vosmem_softmax_dense_scratch_bytes): lets the top_k <= 0 (dense) softmax run parallel over rows too
+extern "C" int vosmem_softmax_dense_ws(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k,
+                                       float *affinity, int64_t aff_ld, float *usage, void *stats_scratch,
+                                       int64_t scratch_bytes, vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(similarity && affinity, "vosmem_softmax_dense: null pointer");
+  if (stats_scratch != nullptr && scratch_bytes < vosmem_softmax_dense_scratch_bytes(n, hw)) stats_scratch = nullptr;
   VOSMEM_CHECK_ARG(n >= 1 && hw >= 1, "vosmem_softmax_dense: n=%lld hw=%d", (long long)n, hw);
   VOSMEM_CHECK_ARG(top_k <= DENSE_MAX_TOPK, "vosmem_softmax_dense: top_k=%d above %d", top_k, DENSE_MAX_TOPK);
   VOSMEM_CHECK_ARG(top_k <= 0 || top_k <= n, "vosmem_softmax_dense: top_k=%d exceeds the %lld memory elements", top_k,
@@ -238,16 +327,38 @@ extern "C" int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int
     softmax_topk_any_kernel<<<(hw + 7) / 8, 256, 0, st>>>(similarity, sim_ld, n, hw, top_k, affinity, aff_ld, usage);
   else if (top_k > 0)
     softmax_topk_dense_kernel<<<grid, 1024, 0, st>>>(similarity, sim_ld, n, hw, top_k, affinity, aff_ld, usage);
-  else
+  else if (stats_scratch != nullptr) {
+    const int chunks = (int)ceil_div64(n, SM_ROWS);
+    dim3 g2((hw + 31) / 32, chunks);
+    softmax_stats_kernel<<<g2, 256, 0, st>>>(similarity, sim_ld, n, hw, static_cast<float2 *>(stats_scratch));
+    softmax_apply_kernel<<<g2, 256, 0, st>>>(similarity, sim_ld, n, hw, static_cast<const float2 *>(stats_scratch), chunks,
+                                             affinity, aff_ld, usage);
+  } else
     softmax_full_dense_kernel<<<grid, 1024, 0, st>>>(similarity, sim_ld, n, hw, affinity, aff_ld, usage);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
+}
+
+extern "C" int vosmem_softmax_dense(const float *similarity, int64_t sim_ld, int64_t n, int hw, int top_k,
+                                    float *affinity, int64_t aff_ld, float *usage, vosmem_stream_t stream) {
+  return vosmem_softmax_dense_ws(similarity, sim_ld, n, hw, top_k, affinity, aff_ld, usage, nullptr, 0, stream);
+}
+
+extern "C" int64_t vosmem_softmax_dense_scratch_bytes(int64_t n, int hw) {
+  return n >= 1 && hw >= 1 ? ceil_div64(n, SM_ROWS) * hw * (int64_t)sizeof(float2) : 0;
 }
 
 extern "C" int vosmem_readout_dense(const float *value, int64_t value_ld, const float *affinity, int64_t aff_ld,
                                     int rows, int64_t n, int hw, float *out, int64_t out_ld, vosmem_stream_t stream) {
   VOSMEM_CHECK_ARG(value && affinity && out, "vosmem_readout_dense: null pointer");
   VOSMEM_CHECK_ARG(rows >= 1 && n >= 1 && hw >= 1, "vosmem_readout_dense: rows=%d n=%lld hw=%d", rows, (long long)n, hw);
+  if (rows <= 8) {
+    VOSMEM_CUDA(cudaMemset2DAsync(out, out_ld * sizeof(float), 0, hw * sizeof(float), rows, (cudaStream_t)stream));
+    readout_few_rows_kernel<<<dim3((hw + 31) / 32, (unsigned)ceil_div64(n, SM_ROWS)), 256, 0, (cudaStream_t)stream>>>(
+        value, value_ld, affinity, aff_ld, rows, n, hw, out, out_ld);
+    VOSMEM_CUDA(cudaGetLastError());
+    return VOSMEM_OK;
+  }
   dim3 grid((hw + DT - 1) / DT, (rows + DT - 1) / DT);
   readout_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(value, value_ld, affinity, aff_ld, rows, n, hw, out,
                                                               out_ld);

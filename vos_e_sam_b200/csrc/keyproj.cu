@@ -33,9 +33,10 @@ constexpr int KP_K8 = KP_KC / 8;     // 16-byte chunks per operand row and K blo
 constexpr int KP_TAPS = 9;
 constexpr int KP_A_STAGES = 2, KP_B_STAGES = 4;
 constexpr int KP_B_BYTES = 2 * KP_K8 * KP_N * 16;     // one (K block, tap) of packed weights: hi + lo = 18 432 B
+template <int NN>
+constexpr int b_bytes() { return 2 * KP_K8 * NN * 16; }
 constexpr int KP_THREADS = 192;      // warps 0-3 epilogue (TMEM lane quarters), warp 4 producer, warp 5 MMA
 constexpr int KP_TMEM_COLS = 256;
-constexpr uint32_t KP_IDESC = ptx::umma_idesc_bf16(KP_M, KP_N);
 
 struct KpGeom {
   int in_dim, h, w, wp, p_pad, q_rows, halo, splits;   // q_rows = p_pad + 2 * (wp + 1)
@@ -114,11 +115,17 @@ __global__ void __launch_bounds__(KP_N) pack_w_kernel(const float *__restrict__ 
 struct KpArgs {
   const unsigned char *xp;   // packed activations
   const unsigned char *wq;   // packed weights
-  float *partial;            // [splits][p_pad][KP_N]
+  float *partial;            // [splits][p_pad][NN]
   KpGeom g;
 };
 
+// NN output columns (a multiple of 16, <= 256), TAPS row-shifted reads of the activation tile per K block.  With
+// TAPS == 1 and a halo of 128 rows this is a plain split-K GEMM  D[128 x NN] += A[128 x K] . B[NN x K]^T  over packed
+// operands, which the dense readout of the consolidation uses (tc_readout_dense below).
+template <int NN, int TAPS>
 __global__ void __launch_bounds__(KP_THREADS, 1) keyproj_mma_kernel(const __grid_constant__ KpArgs a) {
+  constexpr int KP_N = NN, KP_TAPS = TAPS, KP_B_BYTES = b_bytes<NN>();
+  constexpr uint32_t KP_IDESC = ptx::umma_idesc_bf16(KP_M, NN);
   extern __shared__ __align__(128) unsigned char smem[];
   const KpGeom &g = a.g;
   const uint32_t a_stage_bytes = 2u * KP_K8 * g.halo * 16u;   // hi + lo halo tiles of one K block
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(KP_THREADS, 1) keyproj_mma_kernel(const __grid
     float *dst = a.partial + ((int64_t)blockIdx.y * g.p_pad + p0 + warp * 32 + lane) * KP_N;
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 + 32 <= NN; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32(taddr + c0, v);
       ptx::tmem_ld_wait();
@@ -215,14 +222,17 @@ __global__ void __launch_bounds__(KP_THREADS, 1) keyproj_mma_kernel(const __grid
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4 *>(dst + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    uint32_t t0[8], t1[8];
-    ptx::tmem_ld_32x8(taddr + 128, t0);
-    ptx::tmem_ld_32x8(taddr + 136, t1);
-    ptx::tmem_ld_wait();
-    *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(t0[0], t0[1], t0[2], t0[3]);
-    *reinterpret_cast<uint4 *>(dst + 132) = make_uint4(t0[4], t0[5], t0[6], t0[7]);
-    *reinterpret_cast<uint4 *>(dst + 136) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
-    *reinterpret_cast<uint4 *>(dst + 140) = make_uint4(t1[4], t1[5], t1[6], t1[7]);
+    if constexpr (NN % 32 == 16) {
+      constexpr int C0 = NN - 16;
+      uint32_t t0[8], t1[8];
+      ptx::tmem_ld_32x8(taddr + C0, t0);
+      ptx::tmem_ld_32x8(taddr + C0 + 8, t1);
+      ptx::tmem_ld_wait();
+      *reinterpret_cast<uint4 *>(dst + C0) = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+      *reinterpret_cast<uint4 *>(dst + C0 + 4) = make_uint4(t0[4], t0[5], t0[6], t0[7]);
+      *reinterpret_cast<uint4 *>(dst + C0 + 8) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+      *reinterpret_cast<uint4 *>(dst + C0 + 12) = make_uint4(t1[4], t1[5], t1[6], t1[7]);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -295,10 +305,145 @@ int kp_check(int in_dim, int key_dim, int h, int w) {
   return VOSMEM_OK;
 }
 
+// ======================================================================================================================
+// Dense readout on tcgen05:  out[rows x hw] = value[rows x n] @ affinity[n x hw]   (MemoryManager._readout,
+// memory_manager.py:53-55, as consolidation calls it: memory_manager.py:280-284 -- 2 560 x 8 100 @ 8 100 x 128 at the
+// DAVIS shape, 5.3 GFLOP that the 64 x 64 SIMT twin needs 1.6 ms for).  Both operands are packed into bf16 (hi, lo)
+// K-major rows (K = memory elements, zero-padded to a multiple of 32) and go through the split-K GEMM above.
+// ======================================================================================================================
+// value rows x n fp32 (n contiguous) -> [hl][k8][row][8]
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ v, int64_t v_ld, int rows, int64_t n,
+                                                        int rows_pad, int k8_total, uint4 *__restrict__ out) {
+  const int row = blockIdx.x * 256 + threadIdx.x, k8 = blockIdx.y;
+  if (row >= rows_pad) return;
+  uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+  if (row < rows) {
+    const float *src = v + (int64_t)row * v_ld + (int64_t)k8 * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t k = (int64_t)k8 * 8 + 2 * j;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(k < n ? src[2 * j] : 0.f, h0, l0);
+      split_bf16(k + 1 < n ? src[2 * j + 1] : 0.f, h1, l1);
+      hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+  out[(int64_t)k8 * rows_pad + row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  out[((int64_t)k8_total + k8) * rows_pad + row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// affinity n x hw fp32 (hw contiguous) -> [K block][hl][k8][col = NN][8]
+template <int NN>
+__global__ void __launch_bounds__(NN) pack_cols_kernel(const float *__restrict__ aff, int64_t aff_ld, int64_t n, int hw,
+                                                       uint4 *__restrict__ out) {
+  const int col = threadIdx.x, k8 = blockIdx.x % KP_K8, kb = blockIdx.x / KP_K8;
+  uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+  if (col < hw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t k = (int64_t)kb * KP_KC + k8 * 8 + 2 * j;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(k < n ? aff[k * aff_ld + col] : 0.f, h0, l0);
+      split_bf16(k + 1 < n ? aff[(k + 1) * aff_ld + col] : 0.f, h1, l1);
+      hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+  uint4 *blk = out + (int64_t)kb * (b_bytes<NN>() / 16);
+  blk[k8 * NN + col] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  blk[(KP_K8 + k8) * NN + col] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// out[row][col] = sum over the K splits of partial[s][row][col]
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float *__restrict__ partial, int splits, int rows_pad, int nn,
+                                                           int rows, int hw, float *__restrict__ out, int64_t out_ld) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int row = (int)(e / nn), col = (int)(e % nn);
+  if (row >= rows || col >= hw) return;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += partial[((int64_t)s * rows_pad + row) * nn + col];
+  out[(int64_t)row * out_ld + col] = acc;
+}
+
+struct DenseGeom {
+  KpGeom g;
+  int nn, rows_pad;
+  int64_t k_pad, a_bytes, b_bytes_total, partial_bytes, total;
+};
+DenseGeom dense_geom(int rows, int64_t n, int hw) {
+  DenseGeom d{};
+  d.nn = hw <= 64 ? 64 : hw <= 128 ? 128 : 256;
+  d.rows_pad = (int)round_up64(rows, KP_M);
+  KpGeom &g = d.g;
+  {   // K splits: fill the SMs once; the K axis is zero-padded to a whole number of 32-element blocks per split
+    const int tiles = d.rows_pad / KP_M;
+    const int64_t blocks = ceil_div64(n, KP_KC);
+    int64_t s = 148 / tiles;
+    if (s < 1) s = 1;
+    if (s > blocks) s = blocks;
+    g.splits = (int)s;
+    d.k_pad = round_up64(blocks, s) * KP_KC;
+  }
+  g.in_dim = (int)d.k_pad;
+  g.h = g.w = 0;
+  g.wp = -1;                 // no halo: every "tap" shift is zero
+  g.p_pad = d.rows_pad;
+  g.q_rows = d.rows_pad;
+  g.halo = KP_M;
+  d.a_bytes = round_up64((int64_t)2 * (d.k_pad / 8) * d.rows_pad * 16, 256);
+  d.b_bytes_total = round_up64((d.k_pad / KP_KC) * (int64_t)(2 * KP_K8 * d.nn * 16), 256);
+  d.partial_bytes = round_up64((int64_t)g.splits * d.rows_pad * d.nn * 4, 256);
+  d.total = d.a_bytes + d.b_bytes_total + d.partial_bytes;
+  return d;
+}
+
+template <int NN>
+int run_dense_tc(const float *value, int64_t value_ld, const float *aff, int64_t aff_ld, int rows, int64_t n, int hw,
+                 float *out, int64_t out_ld, const DenseGeom &d, unsigned char *ws, cudaStream_t st) {
+  const KpGeom &g = d.g;
+  unsigned char *ap = ws, *bp = ws + d.a_bytes;
+  float *partial = reinterpret_cast<float *>(ws + d.a_bytes + d.b_bytes_total);
+  const int k8_total = (int)(d.k_pad / 8);
+  pack_rows_kernel<<<dim3((d.rows_pad + 255) / 256, k8_total), 256, 0, st>>>(value, value_ld, rows, n, d.rows_pad, k8_total,
+                                                                            reinterpret_cast<uint4 *>(ap));
+  pack_cols_kernel<NN><<<(unsigned)(d.k_pad / KP_KC) * KP_K8, NN, 0, st>>>(aff, aff_ld, n, hw, reinterpret_cast<uint4 *>(bp));
+  KpArgs a{ap, bp, partial, g};
+  const size_t smem = (size_t)KP_A_STAGES * 2 * KP_K8 * g.halo * 16 + (size_t)KP_B_STAGES * b_bytes<NN>() +
+                      (2 * KP_A_STAGES + 2 * KP_B_STAGES + 1) * 8 + 16;
+  VOSMEM_CUDA(cudaFuncSetAttribute(keyproj_mma_kernel<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  keyproj_mma_kernel<NN, 1><<<dim3(d.rows_pad / KP_M, g.splits), KP_THREADS, smem, st>>>(a);
+  sum_partials_kernel<<<(unsigned)ceil_div64((int64_t)rows * NN, 256), 256, 0, st>>>(partial, g.splits, d.rows_pad, NN, rows, hw,
+                                                                                      out, out_ld);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
 }  // namespace
 }  // namespace vosmem
 
 using namespace vosmem;
+
+extern "C" int64_t vosmem_readout_dense_tc_workspace_bytes(int rows, int64_t n, int hw) {
+  if (rows < 1 || n < 1 || hw < 1 || hw > 256 || n > ((int64_t)1 << 24)) return 0;
+  return dense_geom(rows, n, hw).total;
+}
+
+extern "C" int vosmem_readout_dense_tc(const float *value, int64_t value_ld, const float *affinity, int64_t aff_ld, int rows,
+                                       int64_t n, int hw, float *out, int64_t out_ld, void *workspace, int64_t workspace_bytes,
+                                       vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(value && affinity && out && workspace, "vosmem_readout_dense_tc: null pointer");
+  VOSMEM_CHECK_ARG(rows >= 1 && n >= 1 && hw >= 1 && hw <= 256, "vosmem_readout_dense_tc: rows=%d n=%lld hw=%d (hw <= 256)", rows,
+                   (long long)n, hw);
+  const DenseGeom d = dense_geom(rows, n, hw);
+  if (workspace_bytes < d.total) {
+    set_error("readout_dense_tc: workspace of %lld bytes, need %lld", (long long)workspace_bytes, (long long)d.total);
+    return VOSMEM_ENOSPC;
+  }
+  unsigned char *ws = static_cast<unsigned char *>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.nn == 64) return run_dense_tc<64>(value, value_ld, affinity, aff_ld, rows, n, hw, out, out_ld, d, ws, st);
+  if (d.nn == 128) return run_dense_tc<128>(value, value_ld, affinity, aff_ld, rows, n, hw, out, out_ld, d, ws, st);
+  return run_dense_tc<256>(value, value_ld, affinity, aff_ld, rows, n, hw, out, out_ld, d, ws, st);
+}
 
 extern "C" int64_t vosmem_keyproj_weight_bytes(int in_dim, int key_dim) {
   if (key_dim != 64 || in_dim < KP_KC || in_dim % KP_KC != 0) return 0;
@@ -340,8 +485,8 @@ extern "C" int vosmem_keyproj_forward(const float *x, int in_dim, int key_dim, i
   const size_t smem = (size_t)KP_A_STAGES * 2 * KP_K8 * g.halo * 16 + (size_t)KP_B_STAGES * KP_B_BYTES +
                       (2 * KP_A_STAGES + 2 * KP_B_STAGES + 1) * 8 + 16;
   VOSMEM_CHECK_ARG(smem <= 232448, "keyproj: %zu bytes of shared memory for w=%d", smem, w);
-  VOSMEM_CUDA(cudaFuncSetAttribute(keyproj_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  keyproj_mma_kernel<<<dim3(g.p_pad / KP_M, g.splits), KP_THREADS, smem, st>>>(a);
+  VOSMEM_CUDA(cudaFuncSetAttribute(keyproj_mma_kernel<KP_N, KP_TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  keyproj_mma_kernel<KP_N, KP_TAPS><<<dim3(g.p_pad / KP_M, g.splits), KP_THREADS, smem, st>>>(a);
   KpOut o{ws.partial, key_bias, d_bias, e_bias, key, shrinkage, selection, g, key_dim};
   keyproj_finalize_kernel<<<g.p_pad / 32, 128, 0, st>>>(o);
   VOSMEM_CUDA(cudaGetLastError());

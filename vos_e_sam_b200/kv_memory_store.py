@@ -71,8 +71,10 @@ class _Grow:
         """Remove [start, stop) on the last axis."""
         tail = self.n - stop
         if tail > 0 and stop > start:
-            moved = self.buf[..., stop:self.n].clone()
-            self.buf[..., start:start + tail].copy_(moved)
+            src = self.buf[..., stop:self.n]
+            if tail > stop - start:          # source and destination overlap: stage the tail
+                src = src.clone()
+            self.buf[..., start:start + tail].copy_(src)
         self.n -= (stop - start)
 
     def keep(self, index: torch.Tensor) -> None:
@@ -115,8 +117,13 @@ class _ValueGroup:
         self._sync_shadow(begin)
 
     def cut(self, start: int, stop: int) -> None:
+        tail = self.n - stop
         self.ref.cut(start, stop)
-        self._sync_shadow(start)
+        if 0 < tail <= stop - start and self.shadow.shape[0] >= self.ref.capacity:
+            # the shadow rows of the tail move as they are (no overlap): no re-transposition of the fp32 values
+            self.shadow[start:start + tail].copy_(self.shadow[stop:stop + tail])
+        else:
+            self._sync_shadow(start)
 
     def keep(self, index: torch.Tensor) -> None:
         self.ref.keep(index)

@@ -96,7 +96,11 @@ class MemoryManager:
     def _readout(self, affinity, v):
         """Dense readout of one object group (memory_manager.py:53-55); used by consolidation."""
         n_obj, cv, n = v.shape
-        flat = v.reshape(n_obj * cv, n) if v.is_contiguous() else v.contiguous().view(n_obj * cv, n)
+        if v.stride(2) == 1 and (n_obj == 1 or v.stride(0) == cv * v.stride(1)):
+            # a slice of a bank along the key axis (compress_features): rows keep the bank's pitch, nothing is copied
+            flat = v.as_strided((n_obj * cv, n), (v.stride(1), 1))
+        else:
+            flat = v.contiguous().view(n_obj * cv, n)
         return ops.readout_dense(flat, affinity[0]).view(n_obj, cv, -1)
 
     # ------------------------------------------------------------------------------------------------

@@ -319,8 +319,12 @@ def softmax_dense(similarity: Tensor, top_k: Optional[int], inplace: bool, want_
     aff = similarity if inplace else torch.empty((n, hw), dtype=torch.float32, device=similarity.device)
     aff_ld = sim_ld if inplace else hw
     usage = torch.empty(n, dtype=torch.float32, device=similarity.device) if want_usage else None
-    check(N.lib.vosmem_softmax_dense(similarity.data_ptr(), sim_ld, n, hw, top_k if top_k is not None else 0,
-                                     aff.data_ptr(), aff_ld, _p(usage), _stream()), 'vosmem_softmax_dense')
+    scratch = None
+    if top_k is None or top_k <= 0:     # dense softmax: statistics per (row chunk, column) let it run parallel over rows
+        scratch = torch.empty(int(N.lib.vosmem_softmax_dense_scratch_bytes(n, hw)), dtype=torch.uint8, device=similarity.device)
+    check(N.lib.vosmem_softmax_dense_ws(similarity.data_ptr(), sim_ld, n, hw, top_k if top_k is not None else 0,
+                                        aff.data_ptr(), aff_ld, _p(usage), _p(scratch),
+                                        scratch.numel() if scratch is not None else 0, _stream()), 'vosmem_softmax_dense')
     return aff, usage
 
 
@@ -333,6 +337,12 @@ def readout_dense(value: Tensor, affinity: Tensor) -> Tensor:
         raise RuntimeError(f'readout: value has {n} memory elements, affinity {affinity.shape[0]}')
     hw = affinity.shape[1]
     out = torch.empty((rows, hw), dtype=torch.float32, device=value.device)
+    if rows >= 64 and hw <= 256 and n >= 256 and v_ld % 4 == 0:
+        # consolidation-sized products go through the tcgen05 split-K GEMM (csrc/keyproj.cu, tc_readout_dense)
+        ws = torch.empty(int(N.lib.vosmem_readout_dense_tc_workspace_bytes(rows, n, hw)), dtype=torch.uint8, device=value.device)
+        check(N.lib.vosmem_readout_dense_tc(value.data_ptr(), v_ld, affinity.data_ptr(), a_ld, rows, n, hw, out.data_ptr(), hw,
+                                            ws.data_ptr(), ws.numel(), _stream()), 'vosmem_readout_dense_tc')
+        return out
     check(N.lib.vosmem_readout_dense(value.data_ptr(), v_ld, affinity.data_ptr(), a_ld, rows, n, hw, out.data_ptr(), hw,
                                      _stream()), 'vosmem_readout_dense')
     return out
