@@ -248,14 +248,25 @@ struct KpOut {
   int key_dim;
 };
 
+constexpr int KP_FIN_CH = 36;   // channels per finalize CTA (grid.y = KP_N / 36 = 4: enough CTAs to hide the load latency)
 __global__ void __launch_bounds__(128) keyproj_finalize_kernel(const __grid_constant__ KpOut o) {
-  __shared__ float tile[32][KP_N + 1];
+  __shared__ float tile[32][KP_FIN_CH + 1];
   const KpGeom &g = o.g;
-  const int pb = blockIdx.x * 32;
-  for (int e = threadIdx.x; e < 32 * KP_N; e += 128) {
-    float acc = 0.f;
-    for (int s = 0; s < g.splits; ++s) acc += o.partial[((int64_t)s * g.p_pad + pb) * KP_N + e];
-    tile[e / KP_N][e % KP_N] = acc;
+  const int pb = blockIdx.x * 32, n0 = blockIdx.y * KP_FIN_CH;
+  // 16-byte loads, the K splits of an element in flight together (the sum order is fixed: split 0, 1, ...)
+  for (int e = threadIdx.x; e < 32 * (KP_FIN_CH / 4); e += 128) {
+    const int r = e / (KP_FIN_CH / 4), c = (e % (KP_FIN_CH / 4)) * 4;
+    const float4 *src = reinterpret_cast<const float4 *>(o.partial + ((int64_t)pb + r) * KP_N + n0 + c);
+    const int64_t split_stride = (int64_t)g.p_pad * KP_N / 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < g.splits; s0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = s0 + u < g.splits ? src[(s0 + u) * split_stride] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    tile[r][c] = acc.x; tile[r][c + 1] = acc.y; tile[r][c + 2] = acc.z; tile[r][c + 3] = acc.w;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,17 +274,18 @@ __global__ void __launch_bounds__(128) keyproj_finalize_kernel(const __grid_cons
   const int yp = p / g.wp, xq = p % g.wp;
   const bool inside = yp >= 1 && yp <= g.h && xq >= 1 && xq <= g.w;
   const int64_t at = (int64_t)(yp - 1) * g.w + (xq - 1), hw = (int64_t)g.h * g.w;
-  for (int n = warp; n < 2 * o.key_dim + 1; n += 4) {
-    if (!inside) continue;
-    const float v = tile[lane][n];
+  for (int c = warp; c < KP_FIN_CH; c += 4) {
+    const int n = n0 + c;
+    if (!inside || n >= 2 * o.key_dim + 1) continue;
+    const float v = tile[lane][c];
     if (n < o.key_dim) {
       o.key[n * hw + at] = v + o.key_b[n];
     } else if (n == o.key_dim) {
       const float d = v + o.d_b[0];
       if (o.shrinkage) o.shrinkage[at] = d * d + 1.0f;
     } else if (o.selection) {
-      const int c = n - o.key_dim - 1;
-      o.selection[c * hw + at] = 1.0f / (1.0f + expf(-(v + o.e_b[c])));
+      const int ce = n - o.key_dim - 1;
+      o.selection[ce * hw + at] = 1.0f / (1.0f + expf(-(v + o.e_b[ce])));
     }
   }
 }
@@ -488,7 +500,7 @@ extern "C" int vosmem_keyproj_forward(const float *x, int in_dim, int key_dim, i
   VOSMEM_CUDA(cudaFuncSetAttribute(keyproj_mma_kernel<KP_N, KP_TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   keyproj_mma_kernel<KP_N, KP_TAPS><<<dim3(g.p_pad / KP_M, g.splits), KP_THREADS, smem, st>>>(a);
   KpOut o{ws.partial, key_bias, d_bias, e_bias, key, shrinkage, selection, g, key_dim};
-  keyproj_finalize_kernel<<<g.p_pad / 32, 128, 0, st>>>(o);
+  keyproj_finalize_kernel<<<dim3(g.p_pad / 32, KP_N / KP_FIN_CH), 128, 0, st>>>(o);
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }
