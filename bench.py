@@ -16,6 +16,8 @@ One JSON line on stdout (rank 0).  A "step" is one query frame: one match_memory
   roofline_other  the other kernel; roofline_step: the whole step against SURVEY.md section 8d's bytes / flops
   cpu_baseline        the reference (oracle/_ref, staged copy of the unmodified modules) or its oracle port on the host cores
   gpu_eager_baseline  the reference's own torch op sequence on CUDA tensors on the same GPU (secondary line)
+  key_projection      SURVEY 8f-4: the tcgen05 KeyProjection against the reference module on cuDNN, same GPU
+  maintenance         add_memory / consolidation / eager-call wall times (not on the per-frame path)
   other_workloads     BASELINE.json configs[2] (`long_video`) and configs[4] (`davis_batch`), short runs of the same kind
   sharded         BASELINE.json configs[3]: ONE LVOS-scale long-term bank sharded along N over the N ranks (strong scaling),
                   with the in-run 1-GPU unsharded time next to it, efficiency = T1 / (N * TN), and the parity of the sharded
@@ -522,6 +524,92 @@ def gpu_eager_baseline(ctx, workload, calls=10):
         return dict(unavailable=f'{type(exc).__name__}: {exc}'[:200])
 
 
+def key_projection_times(ctx, h=30, w=54, reps=20):
+    """SURVEY section 8f-4, the step right before the readout: vos_e_sam_b200.KeyProjection (one tcgen05 implicit GEMM for
+    key / shrinkage / selection) against the reference module's three cuDNN convolutions (tracker/model/modules.py:194-211)
+    on the same GPU; CUDA-graph replays, L2 flushed before each, median."""
+    import statistics
+    import torch.nn as nn
+    import vos_e_sam_b200 as vos
+
+    class RefKeyProjection(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.key_proj, self.d_proj, self.e_proj = (nn.Conv2d(1024, 64, 3, padding=1), nn.Conv2d(1024, 1, 3, padding=1),
+                                                       nn.Conv2d(1024, 64, 3, padding=1))
+
+        def forward(self, x):
+            return self.key_proj(x), self.d_proj(x) ** 2 + 1, torch.sigmoid(self.e_proj(x))
+
+    def timed(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        ts = []
+        for it in range(reps):
+            ctx.flush.fill_(it & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        return statistics.median(ts[3:])
+
+    x = torch.randn(1, 1024, h, w, device=ctx.dev)
+    ours, ref = vos.KeyProjection(1024, 64).to(ctx.dev), RefKeyProjection().to(ctx.dev)
+    with torch.no_grad():
+        t_ours = timed(lambda: ours(x, True, True))
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        t_fp32 = timed(lambda: ref(x))
+        torch.backends.cudnn.allow_tf32 = True
+        t_tf32 = timed(lambda: ref(x))
+        torch.backends.cudnn.allow_tf32 = old
+    flops = 2.0 * h * w * 1024 * 9 * 129
+    return dict(feature_map=[h, w], us=t_ours, algorithmic_tflops=flops / t_ours * 1e-6, executed_flop_multiplier=3,
+                reference_module_cudnn_fp32_us=t_fp32, reference_module_cudnn_tf32_us=t_tf32,
+                kernels='pack_x_kernel + keyproj_mma_kernel<144, 9> (tcgen05) + keyproj_finalize_kernel')
+
+
+def maintenance_times(ctx, h=30, w=54, n_obj=5, steps=60):
+    """What is NOT in the per-frame number: MemoryManager.add_memory (every mem_every-th frame) without / with the working
+    -> long-term consolidation (memory_manager.py:152-190,211-286), and one eager match_memory call (Python + C call +
+    kernels, device-synchronised wall clock) -- XMem's default bounds, DAVIS shape."""
+    import statistics
+    import vos_e_sam_b200 as vos
+    from tests import synth
+    cfg = xmem_config(max_mid_term_frames=10, min_mid_term_frames=5, max_long_term_elements=10000)
+    m = vos.MemoryManager(cfg)
+    g = torch.Generator().manual_seed(3)
+    plain, consolidate, match = [], [], []
+    for _ in range(steps):
+        k, s, e = synth.keys(g, h * w)
+        v = torch.randn(1, n_obj, CV, h, w, generator=g)
+        a = (k.view(1, CK, h, w).to(ctx.dev), s.view(1, 1, h, w).to(ctx.dev), v.to(ctx.dev), list(range(1, n_obj + 1)))
+        sel = e.view(1, CK, h, w).to(ctx.dev)
+        before = m.work_mem.size
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.add_memory(*a, selection=sel)
+        torch.cuda.synchronize()
+        (consolidate if m.work_mem.size < before + h * w else plain).append((time.perf_counter() - t0) * 1e6)
+        qk, qe = (t.to(ctx.dev) for t in synth.query(g, h, w))
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.match_memory(qk, qe)
+            torch.cuda.synchronize()
+            match.append((time.perf_counter() - t0) * 1e6)
+    med = lambda x: statistics.median(x) if x else None
+    return dict(add_memory_us=med(plain), add_memory_with_consolidation_us=med(consolidate[1:] or consolidate),
+                consolidations=len(consolidate), match_memory_eager_call_us=med(match),
+                note='wall clock per call, device-synchronised on both sides (host launch work included); 5 objects, HW 1620')
+
+
 def pcie_ceiling(ctx, nbytes, copies=20):
     """Raw concurrent D2H ceiling: every rank copies `nbytes` from HBM to pinned host memory `copies` times, no kernels.
     Returns aggregate GB/s (sum over ranks of bytes / slowest rank's time)."""
@@ -723,6 +811,9 @@ def run_ours(args, rank, world, local_rank):
         extra['other_workloads'] = others
         sh = measure_sharded(ctx, Ks, W, args.exchange, 'n', want_e2e=True)
         extra['sharded'] = sh
+        if rank == 0:
+            extra['key_projection'] = key_projection_times(ctx)
+            extra['maintenance'] = maintenance_times(ctx)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

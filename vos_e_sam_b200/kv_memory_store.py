@@ -146,6 +146,7 @@ class KeyValueMemoryStore:
         self.obj_groups: List[List[int]] = []
         self.all_objects: List[int] = []
         self._min_capacity = 0
+        self._version = 0     # bumped by everything that changes sizes or buffers (MemoryManager caches its descriptors on it)
 
     def reserve(self, n_elements: int) -> None:
         """Size every buffer that is allocated from now on for at least `n_elements` memory elements.  With the bank's
@@ -173,6 +174,7 @@ class KeyValueMemoryStore:
     # ---- growth (kv_memory_store.py:36-90) ---------------------------------------------------------
     def add(self, key, value, shrinkage, selection, objects: Optional[List[int]]):
         ops._need(key, 'key')
+        self._version += 1
         device, m = key.device, key.shape[2]
         first = self._k is None
         if first:
@@ -248,6 +250,8 @@ class KeyValueMemoryStore:
     def sieve_by_range(self, start: int, end: int, min_size: int):
         """Keep [0, start) ++ [end, N); `end` follows Python slicing on each tensor's own length
         (0 = to the end).  Values of groups shorter than `min_size` are left alone."""
+        self._version += 1
+
         def bounds(n: int):
             lo = min(start, n)
             hi = n if end == 0 else slice(end, None).indices(n)[0]
@@ -264,6 +268,7 @@ class KeyValueMemoryStore:
                 vg.cut(vlo, vhi)
 
     def remove_obsolete_features(self, max_size: int):
+        self._version += 1
         usage = self.get_usage().flatten()
         values, _ = torch.topk(usage, k=(self.size - max_size), largest=False, sorted=True)
         survived = (usage > values[-1]).nonzero().flatten()

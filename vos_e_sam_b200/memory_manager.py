@@ -75,6 +75,7 @@ class MemoryManager:
 
         self.reset_config = True
         self._scratch = None
+        self._plan = None     # cached C descriptors of the last single-group match_memory (see _match_cached)
         # N-sharded over the ranks of torch.distributed (see the module docstring)
         self._sharded = ShardedMatch(self, config) if str(config.get('vosmem_shard', '')).lower() == 'n' else None
 
@@ -175,6 +176,10 @@ class MemoryManager:
         num_objects x CV x H x W tensor).  See `readout_with_hidden`."""
         if self._sharded is not None:
             return self._sharded.match(query_key, selection, out)
+        if out is None:
+            fast = self._match_cached(query_key, selection)
+            if fast is not None:
+                return fast
         problems, out = self._plan_match(query_key, selection, out)
         hw = out.shape[-2] * out.shape[-1]
         if self._scratch is None or self._scratch[0].shape != (hw, self.top_k) or self._scratch[0].device != out.device:
@@ -189,6 +194,40 @@ class MemoryManager:
             ops.match(p.qk, p.qe, p.segments, p.values, p.rows, self.top_k, out=p.out, path=self.path,
                       scratch=self._scratch)
         return out
+
+    def _match_cached(self, query_key, selection):
+        """The common per-frame call -- one object group, fresh output -- with the C descriptors of the previous frame:
+        between two add_memory calls (mem_every - 1 of mem_every frames) only the query and the output pointers
+        change, so the ~60 descriptor fields, the segment objects and the workspace lookup are not rebuilt.  Stores
+        bump `_version` whenever sizes or buffers change.  Returns None when the call does not fit (several groups)."""
+        import ctypes as C
+        work = self.work_mem
+        if work.num_groups != 1 or query_key.shape[0] != 1:
+            return None
+        use_long = self.enable_long_term and self.long_mem.engaged()
+        h, w = query_key.shape[-2:]
+        device = query_key.device
+        stream = torch.cuda.current_stream(device).cuda_stream
+        key = (work._version, self.long_mem._version if use_long else -1, h, w, stream, selection is None, self.top_k,
+               self.path, device)
+        plan = self._plan
+        if plan is None or plan[0] != key:
+            problems, _ = self._plan_match(query_key, selection, None)
+            if len(problems) != 1:
+                return None
+            p = problems[0]
+            keep: list = []
+            sd = ops._select_desc(p.qk, p.qe, p.segments, self.top_k, 0, self.path, keep)
+            rd = ops._readout_desc(sd.hw, self.top_k, p.rows, p.values, p.out, None)
+            plan = self._plan = (key, sd, rd, p.rows, (keep, p))
+        _, sd, rd, rows, _ = plan
+        qk = ops._need(query_key, 'query_key').flatten(start_dim=2)[0].contiguous()
+        qe = ops._need(selection, 'selection').flatten(start_dim=2)[0].contiguous() if selection is not None else None
+        out = torch.empty((rows, h * w), dtype=torch.float32, device=device)
+        sd.query_key, sd.query_selection = qk.data_ptr(), (qe.data_ptr() if qe is not None else None)
+        rd.out, rd.out_ld = out.data_ptr(), h * w
+        N.check(N.lib.vosmem_match(C.byref(sd), C.byref(rd), None, None, stream), 'vosmem_match')
+        return out.view(rows // self.CV, self.CV, h, w)
 
     def readout_with_hidden(self, query_key, selection):
         """``torch.cat([match_memory(...).unsqueeze(0), get_hidden()], 2)`` -- what the decoder consumes
