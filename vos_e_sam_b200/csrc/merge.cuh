@@ -5,7 +5,8 @@
 namespace vosmem {
 
 constexpr int MERGE_MAX_SPLITS = 16;
-constexpr int MERGE_BUF = 128;
+constexpr int MERGE_ROWS = 16;                    // 32-candidate rows merge_query_small holds in shared memory
+constexpr int MERGE_BUF = (MERGE_ROWS + 1) * 32;  // warp-private scratch entries (scores and indices each)
 
 struct SplitLists {
   const CandEntry *cand;    // [splits][hw_pad][slots]
@@ -156,6 +157,123 @@ __device__ __forceinline__ WarpTop32 merge_query(const SplitLists &L, int q, flo
   return top;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same merge for the common case -- at most 12 lists, at most MERGE_ROWS rows of 32 candidates in all -- written for
+// latency and a small instruction footprint: merge_query above executes ~1 200 instructions ONCE per query out of ~6 000
+// (every phase unrolled over the lists, the sorting networks inlined), and a third of its stall samples in the fused
+// readout were instruction fetch (profiles/r2_davis5_ncu_full_summary.txt).  Here the candidates sit in the warp's
+// shared-memory scratch (row = list or list continuation, column = lane) and every phase is a short rolled loop:
+//   1. all loads up front (counts, thresholds, the first 32 slots of every list); longer lists get continuation rows
+//   2. drop what is below the shared threshold; bisect on the value axis (one warp-wide add per step) for a cut that
+//      leaves between top_k and 32 candidates -- no sorting network
+//   3. compact the survivors to one per lane (ballot + popc), rank them against each other with 32 shuffles, and
+//      scatter by rank: the result is the exact best <= 32, best first, like merge_query's.
+// Returns false (nothing else touched but the scratch) when the case does not fit or the bisection cannot separate the
+// candidates (exact ties around the cut): the caller then runs merge_query.
+__device__ __forceinline__ bool merge_query_small(const SplitLists &L, int q, int top_k, float *bs, int *bi, int lane,
+                                                  WarpTop32 &out) {
+  const int n_l = L.splits;
+  if (n_l > 12) return false;
+  // ---- 1. loads ----
+  int my_cnt = 0;
+  if (lane < n_l) my_cnt = L.cand_count[(int64_t)lane * L.hw_pad + q];
+  float tau = INFINITY;
+  if (L.pub_rows > 0) {
+    const uint32_t epoch = __ldcg(&L.ctl->last);
+    for (int y = lane; y < L.pub_rows; y += 32) tau = fminf(tau, pub_load(L.pub + (int64_t)y * L.hw_pad + q, epoch));
+  } else {
+    tau = -INFINITY;
+  }
+#pragma unroll
+  for (int y = 0; y < 12; ++y) {
+    if (y < n_l) {
+      const CandEntry e = L.cand[((int64_t)y * L.hw_pad + q) * CAND_SLOTS + lane];
+      bs[y * 32 + lane] = e.score;
+      bi[y * 32 + lane] = e.index;
+    }
+  }
+  tau = warp_min(tau);
+  int row_cnt = my_cnt < 32 ? my_cnt : 32;      // lane r: valid entries of row r
+  int rows = n_l;
+  if (__any_sync(FULL, my_cnt > 32)) {          // lists longer than 32 entries: continuation rows (second round trip)
+    for (int y = 0; y < n_l; ++y) {
+      const int cnt = __shfl_sync(FULL, my_cnt, y);
+      for (int off = 32; off < cnt; off += 32) {
+        if (rows == MERGE_ROWS) return false;
+        const CandEntry e = L.cand[((int64_t)y * L.hw_pad + q) * CAND_SLOTS + (off + lane < CAND_SLOTS ? off + lane : 0)];
+        bs[rows * 32 + lane] = e.score;
+        bi[rows * 32 + lane] = e.index;
+        if (lane == rows) row_cnt = cnt - off < 32 ? cnt - off : 32;
+        ++rows;
+      }
+    }
+  }
+  // ---- 2. threshold, then a cut with top_k <= #{score >= cut} <= 32 (columns are lane-private up to the compaction) ----
+  int n_mine = 0;
+  float s_hi = -INFINITY, s_lo = INFINITY;
+  for (int r = 0; r < rows; ++r) {
+    const int c = __shfl_sync(FULL, row_cnt, r);
+    float v = bs[r * 32 + lane];
+    if (lane >= c || !(v >= tau) || bi[r * 32 + lane] == 0x7fffffff) v = -INFINITY;
+    bs[r * 32 + lane] = v;
+    if (v > -INFINITY) { ++n_mine; s_hi = fmaxf(s_hi, v); s_lo = fminf(s_lo, v); }
+  }
+  int n = __reduce_add_sync(FULL, n_mine);
+  float cut = -INFINITY;       // every finite candidate
+  if (n > 32) {
+    float lo = warp_min(s_lo), hi = warp_max(s_hi);   // #{score >= lo} = n >= top_k is kept invariant
+    bool found = false;
+    for (int it = 0; it < 26 && lo < hi; ++it) {
+      const float mid = 0.5f * (lo + hi);
+      int c = 0;
+      for (int r = 0; r < rows; ++r) c += bs[r * 32 + lane] >= mid ? 1 : 0;
+      c = __reduce_add_sync(FULL, c);
+      if (c >= top_k) {
+        lo = mid;
+        if (c <= 32) { found = true; n = c; break; }
+      } else {
+        hi = mid;
+      }
+    }
+    if (!found) return false;
+    cut = lo;
+  }
+  // ---- 3. compaction (one survivor per lane), ranks, scatter by rank ----
+  float *cs = bs + MERGE_ROWS * 32;
+  int *ci = bi + MERGE_ROWS * 32;
+  int pos = 0;
+  for (int r = 0; r < rows; ++r) {
+    const float v = bs[r * 32 + lane];
+    const bool keep = v >= cut && v > -INFINITY;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) {
+      const int dst = pos + __popc(m & ((1u << lane) - 1));
+      cs[dst] = v;
+      ci[dst] = bi[r * 32 + lane];
+    }
+    pos += __popc(m);
+  }
+  __syncwarp();
+  float s = lane < pos ? cs[lane] : -INFINITY;
+  int i = lane < pos ? ci[lane] : 0x7fffffff;
+  int rank = 0;
+#pragma unroll 4
+  for (int t = 0; t < 32; ++t) {
+    const float os = __shfl_sync(FULL, s, t);
+    const int oi = __shfl_sync(FULL, i, t);
+    rank += better(os, oi, s, i) ? 1 : 0;
+  }
+  if (lane >= pos) rank = lane;   // empty lanes keep their place behind the `pos` survivors: the ranks are a permutation
+  __syncwarp();
+  cs[rank] = s;
+  ci[rank] = i;
+  __syncwarp();
+  out.s = cs[lane];
+  out.i = ci[lane];
+  __syncwarp();
+  return true;
+}
+
 // Group mode: lane l holds the l-th best GROUP of query q (top.s = its maximum, top.i = list << 6 | slot, or
 // 0x7fffffff for none).  The best k keys of the query all sit in its best k groups (a key's group scores at least the
 // key), so: read the 8 scores of the lane's group, take the exact best 32 of the 32 group maxima plus every other
@@ -212,11 +330,21 @@ static __device__ __noinline__ WarpTop32 merge_groups_of_query(const SplitLists 
   return expand_groups(L, q, merge_query<MB, true>(L, q, buf_s, buf_i, lane), top_k, lane);
 }
 
+// the general merge, out of line: what merge_query_small hands over to
+template <int MB>
+static __device__ __noinline__ WarpTop32 merge_keys_of_query(const SplitLists L, int q, float *buf_s, int *buf_i, int lane) {
+  return merge_query<MB, false>(L, q, buf_s, buf_i, lane);
+}
+
 // merge + (group mode) expansion: what every consumer of the selection's lists calls
 template <int MB = MERGE_MAX_SPLITS>
 __device__ __forceinline__ WarpTop32 merge_lists_of_query(const SplitLists &L, int q, int top_k, float *buf_s, int *buf_i,
                                                           int lane) {
-  if (L.gscore == nullptr) return merge_query<MB, false>(L, q, buf_s, buf_i, lane);
+  if (L.gscore == nullptr) {
+    WarpTop32 top;
+    if (merge_query_small(L, q, top_k, buf_s, buf_i, lane, top)) return top;
+    return merge_keys_of_query<MB>(L, q, buf_s, buf_i, lane);       // many lists, or exact ties around the cut
+  }
   return merge_groups_of_query<MB>(L, q, top_k, buf_s, buf_i, lane);
 }
 
