@@ -94,6 +94,45 @@ int vosmem_pack_values(const float *value, int64_t value_ld, int rows, int64_t s
                        void *shadow, int64_t shadow_ld, int64_t dst_begin, int shadow_dtype,
                        vosmem_stream_t stream);
 
+/* Append `m` memory elements to a bank in ONE call (KeyValueMemoryStore.add, kv_memory_store.py:36-90, without its
+ * torch.cat re-allocation): keys / shrinkage / selection copied behind the `n` elements the preallocated buffers hold,
+ * use_count = 0 and life_count = 1e-7 for the new elements (:37-38), the tensor-core key image packed for them, and the
+ * values of every object group written both in the reference layout (rows x capacity) and, transposed, into the
+ * gather-friendly shadow.  Two launches (keys, values).  The caller has made sure every buffer holds n + m elements. */
+#define VOSMEM_MAX_GROUPS 8
+typedef struct vosmem_append_group {
+  const float *value;   /* rows x m new values, row pitch value_ld                               */
+  int64_t value_ld;
+  int rows;             /* n_g * CV                                                              */
+  float *ref;           /* rows x capacity fp32, row pitch ref_ld (reference layout)             */
+  int64_t ref_ld;
+  void *shadow;         /* capacity x rows (vosmem_pack_values layout), row pitch shadow_ld      */
+  int64_t shadow_ld;
+  int64_t n;            /* elements this group already holds                                     */
+} vosmem_append_group;
+
+typedef struct vosmem_append_desc {
+  int ck, m;
+  int64_t n;                         /* elements the bank already holds                           */
+  const float *key;                  /* CK x m, row pitch key_ld                                  */
+  int64_t key_ld;
+  const float *shrinkage;            /* m, or NULL                                                */
+  const float *selection;            /* CK x m (row pitch selection_ld), or NULL                  */
+  int64_t selection_ld;
+  float *bank_key;                   /* CK x capacity, row pitch bank_ld                          */
+  int64_t bank_ld;
+  float *bank_shrinkage;             /* capacity, or NULL                                         */
+  float *bank_selection;             /* CK x capacity (row pitch bank_ld), or NULL                */
+  float *bank_use, *bank_life;       /* capacity each, or NULL                                    */
+  void *key_image;                   /* packed image of the bank (CK == 64), or NULL              */
+  int64_t capacity;
+  int value_dtype;                   /* enum vosmem_dtype of the shadows                          */
+  int n_groups;
+  vosmem_append_group group[VOSMEM_MAX_GROUPS];
+} vosmem_append_desc;
+
+int vosmem_store_append(const vosmem_append_desc *desc, vosmem_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * The hot path: MemoryManager.match_memory for one object group
  * (tracker/inference/memory_manager.py:57-150 driving memory_util.py:7-65).

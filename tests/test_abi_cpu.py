@@ -48,6 +48,7 @@ def test_struct_layouts_match_the_header(native):
     assert ctypes.sizeof(native.Segment) == 48
     assert ctypes.sizeof(native.SelectDesc) == 16 + 16 + 8 + 2 * 48 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(native.ValueSegment) == 48
+    assert ctypes.sizeof(native.AppendGroup) == 64 and ctypes.sizeof(native.AppendDesc) == 128 + 8 * 64
     assert ctypes.sizeof(native.ReadoutDesc) == 24 + 2 * 48 + 24 + 16
 
 

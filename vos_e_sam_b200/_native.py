@@ -54,6 +54,21 @@ class PushDesc(C.Structure):
                 ('rank_pub', vp * MAX_RANKS), ('seg0_len', i64), ('index_base1', i64)]
 
 
+MAX_GROUPS = 8
+
+
+class AppendGroup(C.Structure):
+    _fields_ = [('value', vp), ('value_ld', i64), ('rows', C.c_int), ('ref', vp), ('ref_ld', i64), ('shadow', vp),
+                ('shadow_ld', i64), ('n', i64)]
+
+
+class AppendDesc(C.Structure):
+    _fields_ = [('ck', C.c_int), ('m', C.c_int), ('n', i64), ('key', vp), ('key_ld', i64), ('shrinkage', vp),
+                ('selection', vp), ('selection_ld', i64), ('bank_key', vp), ('bank_ld', i64), ('bank_shrinkage', vp),
+                ('bank_selection', vp), ('bank_use', vp), ('bank_life', vp), ('key_image', vp), ('capacity', i64),
+                ('value_dtype', C.c_int), ('n_groups', C.c_int), ('group', AppendGroup * MAX_GROUPS)]
+
+
 class ExchangeDesc(C.Structure):
     _fields_ = [('lists', vp), ('n_lists', C.c_int), ('list_stride', i64), ('first_entry', i64), ('flags', vp),
                 ('seq', C.c_uint32), ('status', vp)]
@@ -77,6 +92,7 @@ SIGNATURES = {
     'vosmem_keyproj_forward': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'vosmem_workspace_init': (C.c_int, [vp, i64, vp]),
     'vosmem_workspace_status': (C.c_int, [vp, vp]),
+    'vosmem_store_append': (C.c_int, [vp, vp]),
     'vosmem_pack_keys': (C.c_int, [vp, i64, vp, C.c_int, i64, i64, vp, i64, vp]),
     'vosmem_pack_values': (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, i64, C.c_int, vp]),
     'vosmem_select_topk': (C.c_int, [C.POINTER(SelectDesc), vp, vp, vp]),

@@ -148,6 +148,85 @@ __global__ void pack_values_kernel(const float *__restrict__ value, int64_t valu
   }
 }
 
+// ---- vosmem_store_append -------------------------------------------------------------------------------------------
+struct AppendKeys {
+  int ck, m;
+  int64_t n, key_ld, selection_ld, bank_ld;
+  const float *key, *shrinkage, *selection;
+  float *bank_key, *bank_shrinkage, *bank_selection, *bank_use, *bank_life;
+  unsigned char *image;
+};
+// thread = new element: copy its key / shrinkage / selection column into the bank, initialise the counters, pack its
+// row of the tensor-core image (from the bank entries this thread has just written)
+__global__ void __launch_bounds__(128) append_keys_kernel(const AppendKeys a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.m) return;
+  const int64_t at = a.n + i;
+  for (int c = 0; c < a.ck; ++c) a.bank_key[(int64_t)c * a.bank_ld + at] = a.key[(int64_t)c * a.key_ld + i];
+  if (a.bank_shrinkage) a.bank_shrinkage[at] = a.shrinkage[i];
+  if (a.bank_selection)
+    for (int c = 0; c < a.ck; ++c) a.bank_selection[(int64_t)c * a.bank_ld + at] = a.selection[(int64_t)c * a.selection_ld + i];
+  if (a.bank_use) a.bank_use[at] = 0.f;          // kv_memory_store.py:37
+  if (a.bank_life) a.bank_life[at] = 1e-7f;      // kv_memory_store.py:38
+  if (a.image == nullptr) return;
+  const float scale = (a.bank_shrinkage ? a.shrinkage[i] : 1.0f) * 0.125f;   // 1 / sqrt(64)
+  unsigned char *tile = a.image + (at / TK) * (int64_t)KEY_TILE_BYTES;
+  const int r = (int)(at % TK);
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    Chunk8 h1, l1, h2, l2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = a.key[(int64_t)(g * 8 + j) * a.key_ld + i];
+      const float x2 = scale * m;
+      const float x1 = x2 * m;
+      split_bf16(x1, h1.v[j], l1.v[j]);
+      split_bf16(x2, h2.v[j], l2.v[j]);
+    }
+    store_chunk(tile, image_offset<TK>(r, g), h1);
+    store_chunk(tile, image_offset<TK>(r, 8 + g), h2);
+    store_chunk(tile, image_offset<TK>(r, 16 + g), l1);
+    store_chunk(tile, image_offset<TK>(r, 24 + g), l2);
+  }
+  Chunk8 t;
+  __nv_bfloat16 hi, lo;
+  split_bf16(scale, hi, lo);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+  t.v[0] = hi; t.v[1] = hi; t.v[2] = lo;
+  store_chunk(tile, image_offset<TK>(r, 32), t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t.v[j] = __float2bfloat16_rn(0.f);
+  store_chunk(tile, image_offset<TK>(r, 33), t);
+}
+
+// values of one group: one read of the new rows x m block, written to the reference layout AND, transposed through
+// shared memory, to the shadow
+template <typename T>
+__global__ void append_values_kernel(const float *__restrict__ value, int64_t value_ld, int rows, int64_t m,
+                                     float *__restrict__ ref, int64_t ref_ld, T *__restrict__ shadow, int64_t shadow_ld,
+                                     int64_t n) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int r = r0 + dy;
+    const int64_t i = i0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && i < m) {
+      v = value[(int64_t)r * value_ld + i];
+      ref[(int64_t)r * ref_ld + n + i] = v;
+    }
+    tile[dy][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int64_t i = i0 + dy;
+    const int r = r0 + threadIdx.x;
+    if (r < rows && i < m) shadow[(n + i) * shadow_ld + r] = to_store<T>(tile[threadIdx.x][dy]);
+  }
+}
+
 __global__ void age_kernel(float *__restrict__ life, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) life[i] += 1.0f;
@@ -197,6 +276,36 @@ extern "C" int vosmem_pack_values(const float *value, int64_t value_ld, int rows
   else
     pack_values_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
         value, value_ld, rows, src_begin, n, static_cast<__nv_bfloat16 *>(shadow), shadow_ld, dst_begin);
+  VOSMEM_CUDA(cudaGetLastError());
+  return VOSMEM_OK;
+}
+
+extern "C" int vosmem_store_append(const vosmem_append_desc *d, vosmem_stream_t stream) {
+  VOSMEM_CHECK_ARG(d != nullptr, "vosmem_store_append: null descriptor");
+  VOSMEM_CHECK_ARG(d->ck >= 1 && d->m >= 1 && d->n >= 0, "vosmem_store_append: ck=%d m=%d n=%lld", d->ck, d->m, (long long)d->n);
+  VOSMEM_CHECK_ARG(d->key && d->bank_key && d->n + d->m <= d->capacity, "vosmem_store_append: %lld + %d elements exceed the capacity %lld",
+                   (long long)d->n, d->m, (long long)d->capacity);
+  VOSMEM_CHECK_ARG((d->bank_shrinkage == nullptr) == (d->shrinkage == nullptr) && (d->bank_selection == nullptr) == (d->selection == nullptr),
+                   "vosmem_store_append: shrinkage / selection must be given exactly when the bank holds them");
+  VOSMEM_CHECK_ARG(d->key_image == nullptr || d->ck == CK_TC, "vosmem_store_append: the key image exists for CK == 64 only");
+  VOSMEM_CHECK_ARG(d->n_groups >= 0 && d->n_groups <= VOSMEM_MAX_GROUPS, "vosmem_store_append: n_groups=%d", d->n_groups);
+  VOSMEM_CHECK_ARG(d->value_dtype == VOSMEM_F32 || d->value_dtype == VOSMEM_BF16, "vosmem_store_append: bad dtype %d", d->value_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  AppendKeys a{d->ck, d->m, d->n, d->key_ld, d->selection_ld, d->bank_ld, d->key, d->shrinkage, d->selection, d->bank_key,
+               d->bank_shrinkage, d->bank_selection, d->bank_use, d->bank_life, static_cast<unsigned char *>(d->key_image)};
+  append_keys_kernel<<<(d->m + 127) / 128, 128, 0, st>>>(a);
+  for (int gi = 0; gi < d->n_groups; ++gi) {
+    const vosmem_append_group &g = d->group[gi];
+    if (g.value == nullptr) continue;     // (a group that receives nothing in this call)
+    VOSMEM_CHECK_ARG(g.ref && g.shadow && g.rows >= 1 && g.shadow_ld >= g.rows, "vosmem_store_append: bad value group %d", gi);
+    dim3 grid((unsigned)ceil_div64(d->m, 32), (unsigned)((g.rows + 31) / 32)), block(32, 8);
+    if (d->value_dtype == VOSMEM_F32)
+      append_values_kernel<float><<<grid, block, 0, st>>>(g.value, g.value_ld, g.rows, d->m, g.ref, g.ref_ld,
+                                                          static_cast<float *>(g.shadow), g.shadow_ld, g.n);
+    else
+      append_values_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(g.value, g.value_ld, g.rows, d->m, g.ref, g.ref_ld,
+                                                                  static_cast<__nv_bfloat16 *>(g.shadow), g.shadow_ld, g.n);
+  }
   VOSMEM_CUDA(cudaGetLastError());
   return VOSMEM_OK;
 }

@@ -126,7 +126,8 @@ struct TcArgs {
   int *cand_count;
   float *gscore;       // GROUPS mode: 8 scores per entry of `cand` (then laid out [virtual split][hw_pad][GSLOTS])
   float *glog;         // GROUPS mode: score logs, VOSMEM_GROUP_LOG records of 8 scores per (virtual split, query)
-  int exp;             // experiment switches (VOSMEM_TC_EXP; 0 in production)
+  int exp;             // measurement switches (VOSMEM_TC_EXP, 0 in production): 1 = GROUPS mode appends nothing (floor of the
+                       // epilogue without its stores), 4 = every CTA returns at entry (scripts/launch_cost.py)
   long long *dbg;      // optional per-CTA cycle counters (32 per CTA), NULL in production
 };
 

@@ -175,6 +175,8 @@ class KeyValueMemoryStore:
     def add(self, key, value, shrinkage, selection, objects: Optional[List[int]]):
         ops._need(key, 'key')
         self._version += 1
+        if self._append_fused(key, value, shrinkage, selection, objects):
+            return
         device, m = key.device, key.shape[2]
         first = self._k is None
         if first:
@@ -227,6 +229,77 @@ class KeyValueMemoryStore:
                     vg = _ValueGroup(gv.shape[0], gv.shape[1], device, self.value_dtype, self._min_capacity)
                     vg.append(gv)
                     self._groups.append(vg)
+
+    def _append_fused(self, key, value, shrinkage, selection, objects) -> bool:
+        """The steady-state add -- every buffer exists and has room, the object groups are the ones the bank already
+        has -- as ONE C call (vosmem_store_append: two launches) instead of a dozen copy / fill / pack launches.
+        Returns False when the call does not fit (first add, new objects, growth): the general path above handles it."""
+        import ctypes as C
+        from . import _native as N
+        k = self._k
+        if k is None or key.shape[0] != 1 or k.lead[0] != 1:
+            return False
+        m, n = key.shape[2], k.n
+        if (shrinkage is None) != (self._s is None) or (selection is None) != (self._e is None):
+            return False
+        bufs = [g for g in (k, self._s, self._e, self._use, self._life) if g is not None]
+        if any(g.n != n or g.capacity < n + m for g in bufs):
+            return False
+        if k.lead[1] == 64 and (self._image is None or self._image.numel() < ops.key_image_bytes(64, k.capacity)):
+            return False
+        # the value blocks of the groups, without copies
+        blocks = []
+        if objects is not None:
+            if not isinstance(value, torch.Tensor) or [o - 1 for o in objects] != self.all_objects:
+                return False                      # new objects (a new group) or a different object list
+            for group, vg in zip(self.obj_groups, self._groups):
+                if group != list(range(group[0], group[0] + len(group))):
+                    return False
+                blocks.append((value[group[0]:group[0] + len(group)], vg))
+        else:
+            if not isinstance(value, list) or len(value) != self.num_groups or any(v is None for v in value):
+                return False
+            blocks = list(zip(value, self._groups))
+        if len(blocks) > N.MAX_GROUPS:
+            return False
+        for v, vg in blocks:
+            if v.shape[0] != vg.n_obj or v.shape[1] != vg.cv or v.shape[2] != m or not v.is_contiguous() or \
+                    vg.ref.capacity < vg.n + m or vg.shadow.shape[0] < vg.ref.capacity or v.dtype != torch.float32:
+                return False
+        key2 = key[0] if key.stride(2) == 1 else key[0].contiguous()
+        d = N.AppendDesc()
+        d.ck, d.m, d.n = k.lead[1], m, n
+        d.key, d.key_ld = key2.data_ptr(), key2.stride(0)
+        keep = [key2]
+        if shrinkage is not None:
+            s2 = ops._need(shrinkage, 'shrinkage').reshape(-1).contiguous()
+            keep.append(s2)
+            d.shrinkage, d.bank_shrinkage = s2.data_ptr(), self._s.buf.data_ptr()
+        if selection is not None:
+            e2 = ops._need(selection, 'selection')[0]
+            e2 = e2 if e2.stride(1) == 1 else e2.contiguous()
+            keep.append(e2)
+            d.selection, d.selection_ld, d.bank_selection = e2.data_ptr(), e2.stride(0), self._e.buf.data_ptr()
+        d.bank_key, d.bank_ld = k.buf.data_ptr(), k.capacity
+        if self._use is not None:
+            d.bank_use, d.bank_life = self._use.buf.data_ptr(), self._life.buf.data_ptr()
+        d.key_image = self._image.data_ptr() if k.lead[1] == 64 else None
+        d.capacity = k.capacity
+        d.value_dtype = ops.DTYPE_CODE[self.value_dtype]
+        d.n_groups = len(blocks)
+        for gi, (v, vg) in enumerate(blocks):
+            g = d.group[gi]
+            v2 = v.reshape(vg.rows, m)
+            keep.append(v2)
+            g.value, g.value_ld, g.rows = v2.data_ptr(), m, vg.rows
+            g.ref, g.ref_ld = vg.ref.buf.data_ptr(), vg.ref.capacity
+            g.shadow, g.shadow_ld, g.n = vg.shadow.data_ptr(), vg.shadow.stride(0), vg.n
+        N.check(N.lib.vosmem_store_append(C.byref(d), ops._stream()), 'vosmem_store_append')
+        for g in bufs:
+            g.n = n + m
+        for _, vg in blocks:
+            vg.ref.n += m
+        return True
 
     # ---- usage (kv_memory_store.py:92-99,158-164) -------------------------------------------------
     def update_usage(self, usage):
