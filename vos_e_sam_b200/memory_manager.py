@@ -219,7 +219,7 @@ class MemoryManager:
             keep: list = []
             sd = ops._select_desc(p.qk, p.qe, p.segments, self.top_k, 0, self.path, keep)
             rd = ops._readout_desc(sd.hw, self.top_k, p.rows, p.values, p.out, None)
-            plan = self._plan = (key, sd, rd, p.rows, (keep, p))
+            plan = self._plan = (key, sd, rd, p.rows, None)   # (the descriptors point into the stores' own buffers)
         _, sd, rd, rows, _ = plan
         qk = ops._need(query_key, 'query_key').flatten(start_dim=2)[0].contiguous()
         qe = ops._need(selection, 'selection').flatten(start_dim=2)[0].contiguous() if selection is not None else None
