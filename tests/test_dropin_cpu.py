@@ -82,3 +82,23 @@ def test_signatures_match_the_reference(ref_paths):
         assert ours == ref, name
     for prop in ('size', 'num_groups', 'key', 'value', 'shrinkage', 'selection'):
         assert isinstance(getattr(vos.KeyValueMemoryStore, prop), property) and isinstance(getattr(RefStore, prop), property)
+
+
+def test_key_projection_is_interchangeable_with_the_reference_module(ref_paths):
+    """vos_e_sam_b200.KeyProjection vs tracker/model/modules.py:194-211: same constructor and forward parameters, the
+    same parameter names and shapes -- a state_dict of one loads into the other (how an XMem checkpoint reaches it)."""
+    import inspect
+    import torch
+    import vos_e_sam_b200 as vos
+    from model.modules import KeyProjection as RefKeyProjection
+    for fn in ('__init__', 'forward'):
+        ours = list(inspect.signature(getattr(vos.KeyProjection, fn)).parameters)
+        ref = list(inspect.signature(getattr(RefKeyProjection, fn)).parameters)
+        assert ours == ref, fn
+    ref, ours = RefKeyProjection(64, 64), vos.KeyProjection(64, 64)
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    ours.load_state_dict(ref.state_dict())
+    ref.load_state_dict(ours.state_dict())
+    assert torch.equal(ours.key_proj.weight, ref.key_proj.weight)
+    with pytest.raises(RuntimeError, match='CUDA'):         # no CPU path
+        ours(torch.zeros(1, 64, 4, 4), True, True)
