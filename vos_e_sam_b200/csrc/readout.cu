@@ -201,12 +201,17 @@ __global__ void __launch_bounds__(RTHREADS, 3) softmax_readout_kernel(const __gr
   const int q0 = blockIdx.x * RQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // --- life_count += 1 over the segments' elements (kv_memory_store.py:99), spread over the CTAs of the first chunk
-  if (blockIdx.y == 0) {
+  // --- life_count += 1 over the segments' elements (kv_memory_store.py:99), spread over the CTAs of the first chunk.
+  //     With 4 queries per CTA only warps 0-3 resolve queries below: the other warps do the ageing meanwhile, so its
+  //     load -> add -> store round trip is off every query's critical path. ---
+  constexpr int AGE_WARP0 = RQ < RTHREADS / 32 ? RQ : 0;               // first warp that ages
+  constexpr int AGE_THREADS = RTHREADS - AGE_WARP0 * 32;
+  if (blockIdx.y == 0 && warp >= AGE_WARP0) {
 #pragma unroll
     for (int sgi = 0; sgi < 2; ++sgi)
       if (sgi < a.n_segments && a.life_count[sgi])
-        for (int64_t i = (int64_t)blockIdx.x * RTHREADS + threadIdx.x; i < a.count[sgi]; i += (int64_t)gridDim.x * RTHREADS)
+        for (int64_t i = (int64_t)blockIdx.x * AGE_THREADS + (threadIdx.x - AGE_WARP0 * 32); i < a.count[sgi];
+             i += (int64_t)gridDim.x * AGE_THREADS)
           a.life_count[sgi][i] += 1.0f;
   }
 
