@@ -765,7 +765,37 @@ def test_dense_softmax_twin_takes_large_top_k(vos):
     assert vos.do_softmax(s2, top_k=64, inplace=True).data_ptr() == s2.data_ptr()
     torch.testing.assert_close(s2.cpu(), orc.topk_affinity(sim, 64), rtol=1e-4, atol=1e-6)
     with pytest.raises(ValueError, match='top_k'):
-        vos.MemoryManager(dict(hidden_dim=64, top_k=40, enable_long_term=False, enable_long_term_count_usage=False))
+        vos.MemoryManager(dict(hidden_dim=64, top_k=513, enable_long_term=False, enable_long_term_count_usage=False))
+
+
+@pytest.mark.parametrize('top_k,n_long', [(40, 0), (64, 500), (100, 500)])
+def test_match_memory_wide_top_k(vos, top_k, n_long):
+    """top_k above the fused path's 32 (the reference takes any k: memory_util.py:46): MemoryManager runs the dense
+    sequence of memory_manager.py:57-150 on the dense kernels.  Two object groups, usage recorded on both banks."""
+    g = torch.Generator().manual_seed(top_k)
+    h, w, cv = 6, 9, 32
+    m, ref = build_manager(vos, g, (h, w), 3, 1, cv, n_long=n_long, value_dtype='fp32', top_k=top_k)
+    for _ in range(2):       # a second object appears: group 1 sees only the later frames
+        k, s, e = synth.keys(g, h * w)
+        v = torch.randn(1, 2, cv, h, w, generator=g)
+        args = (k.view(1, -1, h, w), s.view(1, 1, h, w), v, [1, 2])
+        ref.add_memory(*args, selection=e.view(1, -1, h, w))
+        m.add_memory(*(a.cuda() if isinstance(a, torch.Tensor) else a for a in args), selection=e.view(1, -1, h, w).cuda())
+    assert m.work_mem.num_groups == 2
+    for _ in range(2):
+        qk, qe = synth.query(g, h, w)
+        want = ref.match_memory(qk, qe)
+        got = m.match_memory(qk.cuda(), qe.cuda())
+        assert got.shape == want.shape == (2, cv, h, w)
+        assert orc.rel_err(got.cpu(), want) < 1e-4
+    torch.testing.assert_close(m.work_mem.use_count.cpu().flatten(), ref.work_mem.use_count.flatten(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(m.work_mem.life_count.cpu().flatten(), ref.work_mem.life_count.flatten())
+    if n_long:
+        torch.testing.assert_close(m.long_mem.use_count.cpu().flatten(), ref.long_mem.use_count.flatten(), rtol=1e-4, atol=1e-5)
+    out = torch.zeros(2, cv + 8, h, w, device='cuda')
+    qk, qe = synth.query(g, h, w)
+    view = m.match_memory_into(qk.cuda(), qe.cuda(), out)
+    assert view.data_ptr() == out.data_ptr() and orc.rel_err(view.cpu(), ref.match_memory(qk, qe)) < 1e-4
 
 
 def test_bounded_banks_never_move(vos):

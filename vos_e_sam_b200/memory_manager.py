@@ -32,6 +32,7 @@ from .memory_util import do_softmax, get_similarity
 
 _VALUE_DTYPES = {'bf16': torch.bfloat16, 'bfloat16': torch.bfloat16, 'fp32': torch.float32, 'float32': torch.float32}
 _PATHS = {'auto': N.PATH_AUTO, 'simt': N.PATH_SIMT, 'tcgen05': N.PATH_TCGEN05}
+MAX_WIDE_TOPK = 512       # csrc/dense.cu softmax_topk_any_kernel
 
 
 class MemoryManager:
@@ -40,11 +41,12 @@ class MemoryManager:
     @staticmethod
     def _checked_top_k(config):
         """The fused per-frame path holds one survivor per lane of a warp: top_k <= 32 (XMem ships 30, config.yaml:8).
-        Checked here rather than at the first match_memory; memory_util.do_softmax (the dense twin) takes up to 512."""
+        Wider settings, up to the dense softmax kernel's 512, take `_match_wide` (the reference's own dense sequence on
+        this library's dense kernels: correct, not fast).  Checked here rather than at the first match_memory."""
         top_k = int(config['top_k'])
-        if not 1 <= top_k <= N.MAX_TOPK:
-            raise ValueError(f'vos_e_sam_b200.MemoryManager: top_k={top_k} outside [1, {N.MAX_TOPK}] (the fused readout keeps '
-                             f'one survivor per warp lane; see INTEGRATION.md "Limits")')
+        if not 1 <= top_k <= MAX_WIDE_TOPK:
+            raise ValueError(f'vos_e_sam_b200.MemoryManager: top_k={top_k} outside [1, {MAX_WIDE_TOPK}] (fused readout up to '
+                             f'{N.MAX_TOPK}, dense kernels up to {MAX_WIDE_TOPK}; see INTEGRATION.md "Limits")')
         return top_k
 
     def __init__(self, config):
@@ -174,6 +176,8 @@ class MemoryManager:
         [1 x] num_objects x (CV + CH) x H x W buffer -- the decoder's concatenated input (model/modules.py:232-233) --
         whose channels [0, CV) receive the readout directly; the returned tensor is that view (``None``: a fresh
         num_objects x CV x H x W tensor).  See `readout_with_hidden`."""
+        if self.top_k > N.MAX_TOPK:
+            return self._match_wide(query_key, selection, out)
         if self._sharded is not None:
             return self._sharded.match(query_key, selection, out)
         if out is None:
@@ -194,6 +198,55 @@ class MemoryManager:
             ops.match(p.qk, p.qe, p.segments, p.values, p.rows, self.top_k, out=p.out, path=self.path,
                       scratch=self._scratch)
         return out
+
+    def _match_wide(self, query_key, selection, out):
+        """top_k in (32, 512]: the reference's dense sequence (memory_manager.py:57-150) -- similarity over
+        [long-term | working] keys, per-group top-k softmax over the group's key suffixes, usage from group 0, dense
+        readout -- on csrc/dense.cu's kernels.  Materialises N x HW fp32 like the reference does."""
+        work = self.work_mem
+        h, w = query_key.shape[-2:]
+        if query_key.shape[0] != 1:
+            raise RuntimeError('match_memory expects batch size 1 (inference_core.py:53)')
+        qk = query_key.flatten(start_dim=2)
+        qe = selection.flatten(start_dim=2) if selection is not None else None
+        use_long = self.enable_long_term and self.long_mem.engaged()
+        if use_long:
+            long = self.long_mem
+            n_long = long.size
+            sim = get_similarity(torch.cat([long.key, work.key], -1), torch.cat([long.shrinkage, work.shrinkage], -1), qk, qe)
+        else:
+            n_long = 0
+            sim = get_similarity(work.key, work.shrinkage, qk, qe)
+        n_work = work.size
+        readouts = []
+        for gi, gv in enumerate(work.value):
+            len_l = long.get_v_size(gi) if use_long and gi < long.num_groups else 0
+            len_w = n_work if gi == 0 else work.get_v_size(gi)
+            if len_l == n_long and len_w == n_work:
+                group_sim = sim
+            else:       # the group's candidates: a suffix of each bank (memory_manager.py:83,92-97)
+                group_sim = torch.cat([sim[:, n_long - len_l:n_long], sim[:, n_long + n_work - len_w:]], 1)
+            want_usage = gi == 0 and (use_long or self.enable_long_term)
+            res = do_softmax(group_sim, top_k=self.top_k, inplace=group_sim is not sim or work.num_groups == 1,
+                             return_usage=want_usage)
+            if want_usage:
+                aff, usage = res
+                work.update_usage(usage[:, len_l:].flatten())
+                if use_long and self.enable_long_term_usage:
+                    usage_long = usage.new_zeros(n_long)
+                    usage_long[n_long - len_l:] = usage[0, :len_l]
+                    long.update_usage(usage_long)
+            else:
+                aff = res
+            value = torch.cat([long.value[gi], gv], -1) if len_l else gv
+            readouts.append(self._readout(aff, value))
+        result = torch.cat(readouts, 0).view(-1, self.CV, h, w)
+        if out is None:
+            return result
+        if out.dim() == 5 and out.shape[0] == 1:
+            out = out[0]
+        out[:, :self.CV].copy_(result)
+        return out[:, :self.CV]
 
     def _match_cached(self, query_key, selection):
         """The common per-frame call -- one object group, fresh output -- with the C descriptors of the previous frame:
@@ -472,6 +525,8 @@ def match_memory_batch(managers, query_keys, selections):
     (``vosmem_match_batch``: blockIdx.z = problem).  Managers must share CK == 64, the query size and top_k; anything
     else falls back to one call per manager."""
     managers = list(managers)
+    if any(m.top_k > N.MAX_TOPK for m in managers):       # dense path, one manager at a time
+        return [m.match_memory(k, e) for m, k, e in zip(managers, query_keys, selections)]
     plans = [m._plan_match(k, e) for m, k, e in zip(managers, query_keys, selections)]
     top_k = managers[0].top_k
     hw = plans[0][1].shape[-2] * plans[0][1].shape[-1]
