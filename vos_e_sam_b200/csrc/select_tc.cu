@@ -46,6 +46,8 @@
 //           splits then has at least 33 keys at or above it.  Published values carry the launch epoch (PubEntry),
 //           so nothing has to be reset between launches.  With S splits running concurrently this tracks the
 //           quality of a single pass over all keys, which makes list overflows (and sorting) rare.
+//           With R == 2 (17-32 virtual splits: the DAVIS shape) the splits are combined four at a time instead, which
+//           needs only 6 of a group's 8 published keys: see "Grouped thresholds" at refresh_grouped.
 //
 // Thresholds across ranks (N-sharded bank, vosmem_select_push with rank_pub set).  Sharding the key axis over G ranks
 // would make every rank collect ITS OWN best 33 per query -- G times the appends of a single pass, which is what bounds
@@ -395,6 +397,72 @@ __device__ __forceinline__ void refresh_pass(const PubEntry *pub_row, int vsplit
   }
 }
 
+// "Grouped thresholds" (R == 2, i.e. 17-32 virtual splits, the DAVIS shape): every virtual split publishes its best
+// score too (in `pub2`, free when no thresholds cross ranks), and the refreshers combine the splits four at a time.
+// A group of four has 8 published scores of 8 distinct keys, so its j-th largest published value has j keys of the group
+// at or above it; groups hold disjoint key sets, so the minimum over the groups of their want_g-th largest values is a
+// valid bound as soon as the want_g sum to >= 33.  With 22 virtual splits: five groups give their 6th largest, the
+// remaining pair its 3rd (of 4) -- the bound then sits near overall rank 66 instead of ~120 for the plain minimum of the
+// 22 second-best scores (every split must hold 2 of the best keys for that one), i.e. ~1.8x fewer appends and candidates.
+// The three smallest of a pair's four values, ascending (b1 >= b2 per split after the clamp):
+struct Low3 { float x1, x2, x3; };
+__device__ __forceinline__ Low3 pair_low3(float u1, float u2, float v1, float v2) {
+  u1 = fmaxf(u1, u2);   // (a cut may have published an exact 2nd best above the tracker's best; an entry not yet
+  v1 = fmaxf(v1, v2);   //  written reads -inf)
+  const float s = fminf(u2, v2), S = fmaxf(u2, v2), p = fminf(u1, v1);
+  return Low3{s, fminf(S, p), fmaxf(S, p)};
+}
+// the (9 - want)-th smallest of a group of four = want-th largest of its 8 values, want in {6, 7, 8}
+__device__ __forceinline__ float quad_bound(const Low3 &x, const Low3 &y, int want) {
+  if (want >= 8) return fminf(x.x1, y.x1);
+  if (want == 7) return fminf(fminf(x.x2, y.x2), fmaxf(x.x1, y.x1));
+  return fminf(fminf(x.x3, y.x3), fminf(fmaxf(x.x1, y.x2), fmaxf(x.x2, y.x1)));
+}
+constexpr int GB = 12;   // virtual splits per batch of loads (three groups of four)
+__device__ __forceinline__ void refresh_grouped(const PubEntry *pub_row, const PubEntry *pub2_row, int vsplits, int hw_pad,
+                                                uint32_t epoch, float (&m)[RH]) {
+  // how many keys each group has to vouch for: quads 6 (+ up to 2), the trailing pair 3 (+ 1), 33 in total
+  const int nq = vsplits >> 2, np = (vsplits >> 1) & 1;
+  int deficit = 33 - (6 * nq + 3 * np);
+  deficit = deficit > 0 ? deficit : 0;
+  const int pair_want = 3 + (np && deficit > 0 ? 1 : 0);
+  deficit -= pair_want - 3;
+  const int q_add = nq ? deficit / nq : 0, q_rem = nq ? deficit % nq : 0;   // (vsplits >= 17: q_add + 1 <= 2)
+  for (int y0 = 0; y0 < vsplits; y0 += GB) {
+    uint2 r2[GB][RH], r1[GB][RH];   // pub: 2nd best, pub2: best
+#pragma unroll
+    for (int y = 0; y < GB; ++y) {
+      const int yy = min(y0 + y, vsplits - 1);
+#pragma unroll
+      for (int h = 0; h < RH; ++h) {
+        r2[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub_row + (int64_t)yy * hw_pad + 32 * h));
+        r1[y][h] = __ldcg(reinterpret_cast<const uint2 *>(pub2_row + (int64_t)yy * hw_pad + 32 * h));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < GB / 4; ++g) {
+      const int left = vsplits - (y0 + 4 * g);   // virtual splits from this group's first on (warp-uniform)
+      if (left <= 0) break;
+      const int qi = (y0 >> 2) + g;
+      const int want = 6 + q_add + (qi < q_rem ? 1 : 0);
+#pragma unroll
+      for (int h = 0; h < RH; ++h) {
+        float b1[4], b2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          b2[u] = r2[4 * g + u][h].y == epoch ? __uint_as_float(r2[4 * g + u][h].x) : -INFINITY;
+          b1[u] = r1[4 * g + u][h].y == epoch ? __uint_as_float(r1[4 * g + u][h].x) : -INFINITY;
+        }
+        const Low3 x = pair_low3(b1[0], b2[0], b1[1], b2[1]);
+        float bound;
+        if (left >= 4) bound = quad_bound(x, pair_low3(b1[2], b2[2], b1[3], b2[3]), want);
+        else bound = pair_want >= 4 ? x.x1 : x.x2;
+        m[h] = fminf(m[h], bound);
+      }
+    }
+  }
+}
+
 // Warps 0-7 (256 threads): the query operand of this CTA's 128 queries, written in place as the shared-memory image
 // the tcgen05.cp copies expect.  Row y[q] = [-e | 2 q e | -sum_c e q^2] (memory_util.py:20-27; e = 1 and no last term
 // when there is no selection, :28-32), every fp32 entry as a bf16 (hi, lo) pair; 16-byte chunk order per row:
@@ -467,6 +535,7 @@ __device__ __forceinline__ void pack_query_tile(const TcArgs &a, int qtile, unsi
 template <int R, bool SHARED, bool GROUPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_constant__ TcBatch batch) {
   const TcArgs &a = batch.p[blockIdx.z];
+  constexpr bool PAIRED = !SHARED && R == 2;   // "Grouped thresholds" (refresh_grouped): the best score is published too
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + SM_BAR);
   uint64_t *bar_empty = bar_full + STAGES;
@@ -543,7 +612,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
       for (int h = 0; h < RH; ++h) m[h] = INFINITY;
       // rows per batch sized to the number of virtual splits (2: one CTA per query tile, e.g. batched sequences;
       // 4: two splits, LVOS-size query counts; else 22 at a time), so that no pass re-reads rows for nothing
-      if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
+      if constexpr (PAIRED) refresh_grouped(pub_row, a.pub2 + qtile * TQ + row0 + lane, vsplits, a.hw_pad, epoch, m);
+      else if (vsplits <= 2) refresh_pass<2>(pub_row, vsplits, a.hw_pad, epoch, m);
       else if (vsplits <= 4) refresh_pass<4>(pub_row, vsplits, a.hw_pad, epoch, m);
       else refresh_pass<RB>(pub_row, vsplits, a.hw_pad, epoch, m);
       if (SHARED && (it < 8 || (it & 3) == 0)) {
@@ -760,10 +830,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) select_tc_kernel(const __grid_c
         st.pub = best[R - 1];
         pub_store(pub_mine + lane, st.pub, epoch);
       }
-      if (SHARED) {   // the R2-th best of the same tracker, for the bound shared across ranks
+      if (SHARED || PAIRED) {   // SHARED: the R2-th best of the same tracker, for the bound shared across ranks;
+                                // PAIRED: the best, combined with the 2nd best by the refreshers (refresh_grouped)
         float b2 = best[0];
+        if (SHARED) {
 #pragma unroll
-        for (int u = 1; u < R; ++u) b2 = (u < batch.r2) ? best[u] : b2;
+          for (int u = 1; u < R; ++u) b2 = (u < batch.r2) ? best[u] : b2;
+        }
         if (b2 > pub2) {
           pub2 = b2;
           pub_store(pub2_mine + lane, pub2, epoch);
