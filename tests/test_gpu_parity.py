@@ -103,7 +103,10 @@ def test_select_topk_vs_oracle(vos, path, n, h, w, k):
 
 
 @pytest.mark.parametrize('hw,splits', [(16000, 1), (8160, 2), (6000, 3), (4700, 4), (3700, 5), (2500, 7), (1620, 11),
-                                       (500, 23)])
+                                       (500, 23),
+                                       # R == 2, grouped thresholds (select_tc.cu refresh_grouped): 18 ... 32 virtual splits,
+                                       # i.e. every way the groups of four (+ a pair) share out the 33 keys
+                                       (2000, 9), (1700, 10), (1500, 12), (1400, 13), (1200, 14), (1100, 16)])
 def test_select_tc_every_rank_variant_matches_simt(vos, hw, splits):
     """The tcgen05 kernel is instantiated per published rank R = ceil(33 / (2 * splits)); the query count picks the
     number of key splits (148 SMs / query tiles) and with it the variant.  Every variant must return the candidates
